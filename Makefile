@@ -1,0 +1,31 @@
+# Top-level build: libwrp.so (CUDA kernels + C ABI, sm_100a), libwrphost.so (C++ host mirror of
+# the reference's Dimension/Sector/RadarProcessor API on top of the C ABI), the oracle.
+PKG      := weather-radar-processing_b200
+CSRC     := $(PKG)/csrc
+HOST     := $(PKG)/host
+NVCC     ?= nvcc
+CXX      := g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --use_fast_math
+NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC
+LIB      := $(PKG)/libwrp.so
+OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
+
+all: $(LIB) oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/wrp_internal.h $(CSRC)/wrp_fft.cuh include/wrp.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(CSRC)/wrp_tables.o: $(CSRC)/wrp_tables.cpp $(CSRC)/wrp_internal.h include/wrp.h
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+oracle:
+	$(MAKE) -C oracle liboracle.so
+
+clean:
+	rm -f $(OBJS) $(LIB)
+
+.PHONY: all oracle clean

@@ -1,0 +1,119 @@
+// wrp_internal.h — handle layout and kernel-launch prototypes shared by the
+// translation units of libwrp.  Not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wrp.h"
+
+namespace wrp {
+
+// Host-side tables (wrp_tables.cpp) — the reference's generate_constants (rpv2.cu:222-287).
+struct HostTables {
+    std::vector<float> ham;       // [M][N]  wr(i)*wd(j)*c, rpv2.cu:245-249 (double math, float store)
+    std::vector<float> wr_c;      // [M]     wr(i)*c
+    std::vector<float> wd;        // [N]     wd(j)
+    std::vector<float> taps;      // [ma_taps]
+    std::vector<float> fft_ma;    // [N][2]  forward N-point DFT of the zero-padded taps
+    std::vector<float> tw_m;      // [M][2]  exp(-2*pi*i*t/M)   (forward, range)
+    std::vector<float> tw_n;      // [N][2]  exp(+2*pi*i*t/N)   (inverse, Doppler)
+    double c = 0.0;               // window normalisation constant (negative)
+    float taps_sum = 1.f;         // sum of the float taps (== 1 up to rounding)
+};
+void build_host_tables(int M, int N, int ma_taps, HostTables &t);
+
+// Device tables of the fused kernels.
+struct FusedTables {
+    float *wrc_t = nullptr;  // [R2a][R1a]   wr_c[R2a*a + b] stored as [b][a] (range pass-1 window)
+    float *wd = nullptr;     // [N]
+    float2 *tw_a = nullptr;  // [R2a][R1a]   exp(-2*pi*i*b*ka/M)    range inter-pass twiddles
+    float2 *tw_b = nullptr;  // [32][R1b]    exp(+2*pi*i*l*ka/N)    Doppler inter-pass twiddles
+};
+
+struct StagedBuffers {
+    // all [batch][C][...] ; complex stages float2
+    float2 *s00 = nullptr, *s01 = nullptr, *s02 = nullptr, *s03 = nullptr; // [C][M][N]
+    float *s04 = nullptr, *s08 = nullptr;                                  // [C][M/2][N]
+    float2 *s05 = nullptr, *s06 = nullptr, *s07 = nullptr;                 // [C][M/2][N]
+    float2 *rowsum = nullptr;                                              // [C][M] complex row sums (d_tmp, rpv2.cu:299)
+    float *power = nullptr;                                                // [C][M/2]
+    float *result = nullptr;                                               // [batch][M/2][2] products of the last run
+    float *ham = nullptr;                                                  // [M][N]
+    float2 *fft_ma = nullptr;                                              // [N]
+    float2 *tw_m = nullptr, *tw_n_fwd = nullptr, *tw_n_inv = nullptr;      // twiddle tables
+    int batch_capacity = 0;
+    int last_batch = 0; // sectors of the last staged run (for wrp_dump_stage)
+};
+
+struct RingSlot {
+    void *pinned_in = nullptr;   // max_batch sectors of input
+    float *pinned_out = nullptr; // max_batch result slots
+    void *dev_in = nullptr;
+    float *dev_out = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;     // products of this slot are in pinned_out
+    cudaEvent_t h2d_done = nullptr; // input of this slot is in dev_in
+    int n_sectors = 0;          // >0 while in flight
+    std::vector<int> sector_ids, elev_ids;
+};
+
+} // namespace wrp
+
+struct wrp_handle {
+    wrp_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    int l2_bytes = 0;
+    std::string err;
+
+    wrp::HostTables host;
+    wrp::FusedTables fused;
+    wrp::StagedBuffers staged;
+
+    // range -> Doppler hand-off, [chunk][C][M/2][N] float2, reused chunk after chunk so
+    // it stays L2-resident
+    float2 *x2 = nullptr;
+    float2 *decoded = nullptr; // [chunk][C][M][N] planar scratch for wire input
+    float *power = nullptr;    // [chunk][C][M/2]
+    int chunk = 1;
+
+    cudaStream_t compute_stream = nullptr; // all kernels of the host path run here (owns the scratch)
+    std::vector<wrp::RingSlot> ring;
+    int ring_head = 0; // next slot to submit into
+    int ring_tail = 0; // oldest in-flight slot
+    int ring_inflight = 0;
+
+    unsigned long long launches = 0;
+    bool profiling = false;
+    wrp_profile prof{};
+    struct PendingEvent {
+        cudaEvent_t a, b;
+        int kind;
+    };
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace wrp {
+
+// Fused path (wrp_fused.cu).  Each returns cudaGetLastError() after the launch.
+bool fused_supported(int M, int N);
+cudaError_t fused_setup(); // cudaFuncSetAttribute for the big-smem kernels
+cudaError_t launch_decode_wire(const uint8_t *wire, float2 *planar, int M, int N, int C, int n_sectors,
+                               cudaStream_t st);
+cudaError_t launch_range_fft(const float2 *iq, float2 *x2, const FusedTables &t, int M, int N, int C,
+                             int n_sectors, cudaStream_t st);
+cudaError_t launch_doppler(const float2 *x2, float *out, float *power, const FusedTables &t, int M, int N,
+                           int C, int n_sectors, float range_res, float calib, float taps_sum,
+                           cudaStream_t st);
+
+// Staged path (wrp_staged.cu): the reference cascade, one stage per kernel.
+// Returns the number of kernels launched through *launches.
+cudaError_t staged_setup();
+cudaError_t run_staged(wrp_handle *h, const void *dev_in, int n_sectors, float *dev_out, cudaStream_t st,
+                       unsigned long long *launches);
+
+} // namespace wrp
