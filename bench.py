@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — sectors/s of the per-sector weather-radar chain on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic sectors:
+default sector shape 1024 x 512 x 3 (rpv2.cu:38-45), ``--sectors`` sectors per GPU per step.
+
+ours:
+  value      whole-job sectors/s with the batch already resident in HBM as planar complex
+             float — the reference's own device format (rpv2.cu:379-381) — through
+             wrp_process_device (CUDA events on the launching stream, max over ranks).
+  e2e        the same metric through the public host-buffer call wrp_process_host with
+             pinned HOST buffers in the radar's wire format (what the reference's
+             read_matrix receives, sector.cpp:52-62): H2D of every step's input and D2H of
+             its products are inside the timed region.
+  roofline   dominant kernel (range FFT) against the measured HBM copy bandwidth in
+             MEASURED_PEAKS.json: algorithmic bytes per launch / mean launch time (CUDA events
+             recorded around every launch inside the timed region).
+  cpu_baseline  the oracle's float chain (CPU port of read_single.cc) on all host cores,
+             bounded sample.  The oracle is only the baseline/checker here, never the product.
+reference:
+  the reference's own CPU program (oracle/_ref/read_single_ref = unmodified read_single.cc
+  built against the FFTW/UDP shims; falls back to the oracle port when _ref was not built)
+  on all host cores; rank 0 only.
+
+Multi-GPU (torchrun, one rank per GPU): sectors are independent, each rank
+processes its own shard — weak scaling — and the product volume is all-gathered over NCCL
+inside the step; there is no other collective.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, N, C = 1024, 512, 3
+ALGO_BYTES_C64 = C * M * N * 8 + (M // 2) * 8      # 12 587 008
+ALGO_BYTES_WIRE = M * N * 12 + (M // 2) * 8        # 6 295 552
+WORKLOAD = "default sector 1024x512x3 (rpv2.cu:38-45), batch of sectors, fused chain"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_port(sample_sectors: int):
+    """Oracle float chain (port of read_single.cc) on all host cores, wire-format input."""
+    import oracle
+    synth = importlib.import_module("weather-radar-processing_b200.synth")
+    cores = os.cpu_count() or 1
+    wire = synth.make_batch(M, N, sample_sectors, fmt="wire", distinct=2)
+    oracle.batch_wire_f32(wire[:1], 1, M, N, C, 1)  # warm the page cache / libm
+    t0 = time.perf_counter()
+    _, used = oracle.batch_wire_f32(wire, sample_sectors, M, N, C, 0)
+    dt = time.perf_counter() - t0
+    return {"value": sample_sectors / dt, "unit": "sectors/s", "cores": used, "kind": "port",
+            "sample": f"{sample_sectors} synthetic wire-format sectors 1024x512x3, oracle float chain "
+                      f"(OpenMP over sectors, {used} threads), {dt:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU program on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    synth = importlib.import_module("weather-radar-processing_b200.synth")
+    cores = os.cpu_count() or 1
+    exe = os.path.join(ROOT, "oracle", "_ref", "read_single_ref")
+    per_proc = 2
+    steps, warmup = args.steps, args.warmup
+    if os.path.exists(exe):
+        kind = "reference"
+        tmp = tempfile.mkdtemp(prefix="wrp_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        inp = os.path.join(tmp, "wire.bin")
+        synth.make_batch(M, N, per_proc, fmt="wire").tofile(inp)
+
+        def one_step():
+            procs = []
+            for p in range(cores):
+                env = dict(os.environ, WRP_FAKE_UDP_IN=inp, WRP_FAKE_UDP_OUT=os.path.join(tmp, f"o{p}"))
+                procs.append(subprocess.Popen([exe], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env))
+            for p in procs:
+                if p.wait() != 0:
+                    raise RuntimeError("read_single_ref failed")
+            return cores * per_proc
+        desc = (f"{cores} concurrent processes of oracle/_ref/read_single_ref (unmodified read_single.cc, "
+                f"float, hh+vv+vh, FFTW replaced by oracle/shim), {per_proc} wire-format sector each per step")
+    else:
+        kind = "port"
+        import oracle
+        n = max(cores, 8)
+        wire = synth.make_batch(M, N, n, fmt="wire", distinct=2)
+
+        def one_step():
+            oracle.batch_wire_f32(wire, n, M, N, C, 0)
+            return n
+        desc = f"oracle float chain (port of read_single.cc), OpenMP {cores} threads, {n} sectors per step"
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        done += one_step()
+    dt = time.perf_counter() - t0
+    v = done / dt
+    line = {
+        "impl": "reference", "metric": "sectors_per_s", "value": v, "unit": "sectors/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sectors_per_step": done // steps, "input_fmt": "wire_i16be",
+                   "M": M, "N": N, "channels": C},
+        "cpu_baseline": {"value": v, "unit": "sectors/s", "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": "sectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    wrp = importlib.import_module("weather-radar-processing_b200")
+    synth = wrp.synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S = args.sectors
+    steps, warmup = args.steps, args.warmup
+
+    # ---- inputs: a few distinct synthetic sectors tiled to the batch; larger than L2 --------
+    planar = synth.make_batch(M, N, S, fmt="planar", first_sector=rank * 7, distinct=4)
+    d_in = torch.from_numpy(planar.view(np.float32).reshape(-1)).to(dev)
+    d_out = torch.empty((S, M // 2, 2), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * S, M // 2, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    chain = wrp.RadarChain(local_rank, max_batch=args.host_piece)
+    info = chain.info
+    stream = torch.cuda.current_stream()
+
+    def step():
+        chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 1)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    chain.profile_read(reset=True)
+    chain.profile_enable(True)
+    l0 = chain.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = chain.launch_count - l0
+    chain.profile_enable(False)
+    prof = chain.profile_read(reset=True)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * S * steps / (ms * 1e-3)
+
+    # sanity: products finite beyond gate 0
+    host = d_out.cpu().numpy()
+    if not np.isfinite(host[:, 1:, :]).all():
+        raise SystemExit("bench.py: non-finite products")
+
+    # ---- e2e: host wire-format buffers through wrp_process_host -------------------------------
+    wire_chain = wrp.RadarChain(local_rank, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=args.host_piece,
+                                n_streams=args.streams)
+    S2 = args.e2e_sectors
+    wire_np = synth.make_batch(M, N, S2, fmt="wire", first_sector=rank * 7, distinct=4)
+    pin_in = wrp.PinnedBuffer(wire_np.nbytes)
+    pin_in.array[:] = wire_np.reshape(-1)
+    out_e2e = np.empty((S2, M // 2, 2), np.float32)
+    for _ in range(max(warmup, 1)):
+        wire_chain.process_host(pin_in, S2, out_e2e)
+    barrier()
+    l1 = wire_chain.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        wire_chain.process_host(pin_in, S2, out_e2e)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches_e2e = wire_chain.launch_count - l1
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * S2 * steps / dt
+    clocks = sampler.stop()
+
+    # cross-check: the wire path and the planar path see the same sectors -> same products
+    n_chk = min(S, S2, 4)
+    if not np.allclose(out_e2e[:n_chk, 1:], host[:n_chk, 1:], rtol=0, atol=1e-3):
+        raise SystemExit("bench.py: e2e (wire) and HBM-resident (planar) products disagree")
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        n_range = max(int(prof.n_range), 1)
+        sectors_per_launch = S * steps / n_range
+        range_ms = prof.ms_range / n_range
+        achieved = sectors_per_launch * ALGO_BYTES_C64 / (range_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "latest_summary.json")) as f:
+                traffic = json.load(f).get("range_fft_dram_bytes_per_launch")
+        except Exception:
+            pass
+        chain_gbs = value / world * ALGO_BYTES_C64 / 1e9
+        cpu = cpu_baseline_port(args.cpu_sample if args.cpu_sample > 0 else max(2 * (os.cpu_count() or 1), 16))
+        line = {
+            "metric": "sectors_per_s", "value": value, "unit": "sectors/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sectors_per_step_per_gpu": S, "input_fmt": "c64_planar",
+                       "M": M, "N": N, "channels": C, "chunk_sectors": int(info.chunk_sectors),
+                       "l2": f"input batch {d_in.numel() * 4 / 1e6:.0f} MB per GPU > L2 {info.l2_bytes / 1e6:.0f} MB, no flush needed",
+                       "parallelism": f"sectors sharded over {world} GPU(s), products all-gathered"},
+            "iq_gbs": value * ALGO_BYTES_C64 / 1e9,
+            "chain_hbm_frac": chain_gbs / peak,
+            "roofline": {"bound": "hbm", "kernel": "range_fft_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": sectors_per_launch * ALGO_BYTES_C64,
+                         "mean_launch_ms": range_ms,
+                         "kernel_share_of_step": prof.ms_range / ms,
+                         "doppler_mean_launch_ms": prof.ms_doppler / max(int(prof.n_doppler), 1)},
+            "e2e": {"value": e2e_value, "unit": "sectors/s", "h2d_bytes_per_step": S2 * M * N * 12,
+                    "d2h_bytes_per_step": S2 * M * 4, "input_fmt": "wire_i16be", "sectors_per_step_per_gpu": S2,
+                    "h2d_gbs": e2e_value / world * M * N * 12 / 1e9, "api": "wrp_process_host"},
+            "gpu_launches": int(launches + launches_e2e),
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sectors", type=int, default=64, help="sectors per GPU per step (HBM-resident leg)")
+    ap.add_argument("--e2e-sectors", type=int, default=64, help="sectors per GPU per step (host leg)")
+    ap.add_argument("--host-piece", type=int, default=8, help="sectors per pinned-ring piece")
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

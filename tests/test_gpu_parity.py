@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the C ABI of include/wrp.h) against the oracle, the golden
+vectors of the unmodified reference, and size-independent properties.  Needs a B200.
+
+Tolerances (written out here): per stage relL2 <= 1e-4 and row-max-relative <= 1e-4
+against the double-precision oracle; |dZdB|, |dZDR| <= 0.01 dB; gate 0 ZdB is -inf in both."""
+import numpy as np
+import pytest
+
+from conftest import DB_TOL, assert_products_close, assert_stage_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+M, N = 1024, 512
+COMPLEX_STAGES = {"01hamm": "s01_hamm", "02fft1": "s02_fft1", "03fft2": "s03_fft2", "05fft3": "s05_fft3",
+                  "06mult": "s06_mult", "07conv": "s07_conv"}
+REAL_STAGES = {"04abs": "s04_abs", "08pow": "s08_pow", "power": "power"}
+
+
+@pytest.fixture(scope="module")
+def sectors(wrp):
+    return [wrp.synth.make_sector_int16(M, N, s, e) for s, e in ((0, 0), (1, 0), (7, 3))]
+
+
+@pytest.fixture(scope="module")
+def refs(wrp, oracle, sectors):
+    return [oracle.chain(wrp.synth.to_planar(x).astype(np.complex128), dumps=True) for x in sectors]
+
+
+def test_native_library_is_the_one_running(wrp):
+    with wrp.RadarChain(0) as ch:
+        assert ch.info.sm_count >= 100 and ch.launch_count == 0
+        x = wrp.synth.make_batch(M, N, 1, fmt="planar")
+        ch.process_host(x, 1)
+        assert ch.launch_count == 2  # range FFT + Doppler kernels
+
+
+@pytest.mark.parametrize("fmt", ["planar", "wire"])
+def test_fused_products_match_oracle(wrp, sectors, refs, fmt):
+    if fmt == "planar":
+        data = np.stack([wrp.synth.to_planar(x) for x in sectors])
+        kw = {}
+    else:
+        data = np.stack([wrp.synth.to_wire(x) for x in sectors])
+        kw = {"input_fmt": wrp.FMT_WIRE_I16BE}
+    with wrp.RadarChain(0, **kw) as ch:
+        out = ch.process_host(data, len(sectors))
+    for s, ref in enumerate(refs):
+        assert_products_close(out[s], ref.zdb, ref.zdr, f"{fmt} sector {s}")
+        # the reference's own acceptance metric (error.cpp:15-32) on ZdB
+        fin = np.isfinite(ref.zdb)
+        assert rel_l2(out[s][fin, 0], ref.zdb[fin]) < 1e-5
+
+
+def test_fused_matches_unmodified_reference_golden(wrp, golden_ref_run):
+    """Products against the literal read.cc run (double) and read_single.cc datagrams (float)."""
+    g = golden_ref_run
+    iq16 = wrp.synth.make_sector_int16(M, N, 0, 0)
+    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE) as ch:
+        out = ch.process_host(wrp.synth.to_wire(iq16)[None], 1)[0]
+    assert_products_close(out, g["zdb"], g["zdr"], "read.cc golden")
+    zdb32 = g["rs_zdb_packet"][2:].copy().view(">f4").astype(np.float64)
+    zdr32 = g["rs_zdr_packet"][2:].copy().view(">f4").astype(np.float64)
+    assert_products_close(out, zdb32, zdr32, "read_single.cc golden")
+    # and our serialised packets carry the same header/body layout as the reference's
+    zb, zr = wrp.pack_products(out, sector=0, with_elev=False)
+    assert len(zb) == g["rs_zdb_packet"].size and zb[:2] == g["rs_zdb_packet"][:2].tobytes()
+    ours = np.frombuffer(zb[2:], ">f4").astype(np.float64)
+    assert np.max(np.abs(ours[1:] - zdb32[1:])) <= DB_TOL
+
+
+def test_staged_every_stage_matches_oracle(wrp, sectors, refs):
+    data = np.stack([wrp.synth.to_planar(x) for x in sectors[:2]])
+    with wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=2) as ch:
+        out = ch.process_host(data, 2)
+        for s in range(2):
+            assert_products_close(out[s], refs[s].zdb, refs[s].zdr, f"staged sector {s}")
+            assert np.array_equal(ch.dump_stage("09zdb", s)[1:], out[s][1:, 0])
+            assert np.array_equal(ch.dump_stage("10zdr", s), out[s][:, 1])
+            for c in range(3):
+                assert np.array_equal(ch.dump_stage("00iq", s, c), data[s, c])
+                for st, name in COMPLEX_STAGES.items():
+                    got = ch.dump_stage(st, s, c).astype(np.complex128)
+                    assert_stage_close(got, refs[s].stages[name][c], f"{st} s{s} c{c}")
+                for st, name in REAL_STAGES.items():
+                    got = ch.dump_stage(st, s, c).astype(np.float64)
+                    assert_stage_close(got, refs[s].stages[name][c], f"{st} s{s} c{c}")
+
+
+def test_staged_matches_reference_golden_stages(wrp, golden_ref_run):
+    """Stage dumps against the spied stage data of the unmodified read.cc (hh, vv)."""
+    g = golden_ref_run
+    iq16 = wrp.synth.make_sector_int16(M, N, 0, 0)
+    with wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=1, n_channels=2) as ch:
+        ch.process_host(wrp.synth.to_planar(iq16, 2)[None], 1)
+        rf, rh, cols = g["rows_full"], g["rows_half"], g["cols"]
+        for c in range(2):
+            for st, key, rows in [("01hamm", "s01_rows", rf), ("02fft1", "s02_rows", rf), ("03fft2", "s03_rows", rf),
+                                  ("04abs", "s04_rows", rh), ("05fft3", "s05_rows", rh), ("06mult", "s06_rows", rh),
+                                  ("07conv", "s07_rows", rh), ("08pow", "s08_rows", rh)]:
+                got = ch.dump_stage(st, 0, c)[rows]
+                want = g[key][c]
+                den = np.abs(want).max(axis=-1, keepdims=True)
+                assert np.max(np.abs(got - want) / den) <= 1e-4, (st, c)
+            assert rel_l2(ch.dump_stage("02fft1", 0, c)[:, cols], g["s02_cols"][c]) <= 1e-4
+            assert rel_l2(ch.dump_stage("power", 0, c), g["power_hh" if c == 0 else "power_vv"]) <= 1e-5
+
+
+def test_staged_generic_sizes(wrp, oracle):
+    """The staged cascade is generic over power-of-two M, N (the reference is not: §5)."""
+    rng = np.random.default_rng(3)
+    for (m, n, c) in [(64, 32, 3), (256, 1024, 2), (2048, 64, 1), (8, 8, 2)]:
+        x = (rng.integers(-3000, 3000, (2, c, m, n)) + 1j * rng.integers(-3000, 3000, (2, c, m, n))).astype(np.complex64)
+        with wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=2, n_rows_M=m, n_cols_N=n, n_channels=c) as ch:
+            out = ch.process_host(x, 2)
+            for s in range(2):
+                ref = oracle.chain(x[s].astype(np.complex128), dumps=True)
+                got = ch.dump_stage("08pow", s, 0).astype(np.float64)
+                assert_stage_close(got, ref.stages["s08_pow"][0], f"08 {m}x{n}")
+                fin = np.isfinite(ref.zdb)
+                assert np.max(np.abs(out[s][fin, 0] - ref.zdb[fin])) <= DB_TOL
+                if c >= 2:
+                    assert np.max(np.abs(out[s][:, 1] - ref.zdr)) <= DB_TOL
+
+
+def test_fused_equals_staged(wrp, sectors):
+    data = np.stack([wrp.synth.to_planar(x) for x in sectors])
+    with wrp.RadarChain(0) as f, wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=3) as st:
+        a, b = f.process_host(data, 3), st.process_host(data, 3)
+    assert np.max(np.abs(a[:, 1:] - b[:, 1:])) <= 1e-3
+
+
+@pytest.mark.parametrize("channels", [1, 2])
+def test_fewer_channels(wrp, oracle, sectors, channels):
+    data = np.stack([wrp.synth.to_planar(x, channels) for x in sectors[:2]])
+    with wrp.RadarChain(0, n_channels=channels) as ch:
+        out = ch.process_host(data, 2)
+    for s in range(2):
+        ref = oracle.chain(data[s].astype(np.complex128))
+        assert np.isneginf(out[s][0, 0])
+        assert np.max(np.abs(out[s][1:, 0] - ref.zdb[1:])) <= DB_TOL
+        if channels == 2:
+            assert np.max(np.abs(out[s][:, 1] - ref.zdr)) <= DB_TOL
+        else:
+            assert np.all(out[s][:, 1] == 0)
+    # wire input with two channels skips vh on the device
+    wire = np.stack([wrp.synth.to_wire(x) for x in sectors[:2]])
+    if channels == 2:
+        with wrp.RadarChain(0, n_channels=2, input_fmt=wrp.FMT_WIRE_I16BE) as ch:
+            out2 = ch.process_host(wire, 2)
+        assert np.array_equal(out2, out)
+
+
+def test_batch_edges_and_chunking(wrp, sectors, refs):
+    """Empty batch, single sector, batches larger than the internal chunk and than the ring piece,
+    ragged tail; results independent of batching."""
+    one = wrp.synth.to_planar(sectors[0])
+    with wrp.RadarChain(0, max_batch=4) as ch:
+        chunk = ch.info.chunk_sectors
+        assert ch.process_host(one[None], 0).shape == (0, M // 2, 2)
+        single = ch.process_host(one[None], 1)
+        n = 2 * chunk + 3
+        batch = np.stack([wrp.synth.to_planar(sectors[i % 3]) for i in range(n)])
+        out = ch.process_host(batch, n)
+        for i in range(n):
+            assert_products_close(out[i], refs[i % 3].zdb, refs[i % 3].zdr, f"batch item {i}")
+        assert np.array_equal(out[0], single[0])
+        assert np.array_equal(out[3], out[0]) and np.array_equal(out[n - 1], out[(n - 1) % 3])
+        with pytest.raises(wrp.WrpError):
+            ch.process_host(one[None], -1)
+        with pytest.raises(ValueError):
+            ch.process_host(one[None], 2)  # buffer too small for two sectors
+
+
+def test_submit_collect_ring(wrp, sectors, refs):
+    """The reference's sector loop (rpv2.cu:665-683): submit sector k+1 before collecting k; tags
+    (sector, elevation) come back with the products; a full ring reports WRP_ERR_FULL."""
+    wire = [wrp.synth.to_wire(x) for x in sectors]
+    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE, n_streams=2, max_batch=2) as ch:
+        out, sid, eid = ch.collect()
+        assert len(out) == 0
+        ch.submit(wire[0][None], 1, [142], [8])
+        ch.submit(np.stack([wire[1], wire[2]]), 2, [0, 1], [0, 0])
+        with pytest.raises(wrp.WrpError) as ei:
+            ch.submit(wire[0][None], 1)
+        assert ei.value.status == 6
+        with pytest.raises(wrp.WrpError):
+            ch.process_host(wire[0][None], 1)  # submissions pending
+        out, sid, eid = ch.collect()
+        assert sid.tolist() == [142] and eid.tolist() == [8]
+        assert_products_close(out[0], refs[0].zdb, refs[0].zdr, "ring 0")
+        ch.submit(wire[0][None], 1, [5], [1])
+        out, sid, eid = ch.collect()
+        assert sid.tolist() == [0, 1]
+        assert_products_close(out[0], refs[1].zdb, refs[1].zdr, "ring 1")
+        assert_products_close(out[1], refs[2].zdb, refs[2].zdr, "ring 2")
+        out, sid, eid = ch.collect()
+        assert sid.tolist() == [5] and eid.tolist() == [1]
+        with pytest.raises(wrp.WrpError):
+            ch.submit(np.stack(wire), 3)  # more than max_batch
+
+
+def test_pinned_and_pageable_sources_agree(wrp, sectors):
+    wire = np.stack([wrp.synth.to_wire(x) for x in sectors])
+    pin = wrp.PinnedBuffer(wire.nbytes)
+    pin.array[:] = wire.reshape(-1)
+    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=2) as ch:
+        a = ch.process_host(wire, 3)
+        b = ch.process_host(pin, 3)
+    pin.close()
+    assert np.array_equal(a, b)
+
+
+def test_device_resident_path_with_torch_buffers(wrp, sectors, refs):
+    torch = pytest.importorskip("torch")
+    data = np.stack([wrp.synth.to_planar(x) for x in sectors])
+    d_in = torch.from_numpy(data.view(np.float32).reshape(-1)).cuda()
+    d_out = torch.empty((3, M // 2, 2), device="cuda")
+    side = torch.cuda.Stream()
+    with wrp.RadarChain(0) as ch:
+        with torch.cuda.stream(side):
+            ch.process_device(d_in.data_ptr(), 3, d_out.data_ptr(), side.cuda_stream)
+        side.synchronize()
+        first = d_out.cpu().numpy().copy()
+        ch.process_device(d_in.data_ptr(), 3, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+    for s in range(3):
+        assert_products_close(first[s], refs[s].zdb, refs[s].zdr, f"device {s}")
+    assert np.array_equal(first, d_out.cpu().numpy())  # deterministic, stream-independent
+
+
+def test_constants_match_oracle(wrp, oracle):
+    with wrp.RadarChain(0) as ch:
+        ham, taps, fft_ma = ch.constants()
+    ham64, _ = oracle.hamming(M, N)
+    assert np.allclose(ham, ham64, rtol=2e-7)
+    assert np.allclose(taps, oracle.ma_taps(7), rtol=2e-7)
+    assert np.max(np.abs(fft_ma - oracle.ma_fft(7, N))) < 2e-7
+
+
+# ---- size-independent properties at full size ------------------------------------------------
+def test_linearity_in_power(wrp, sectors):
+    """Scaling the IQ by 2 raises ZdB by 20*log10(2) and leaves ZDR alone."""
+    x = wrp.synth.to_planar(sectors[0])
+    with wrp.RadarChain(0) as ch:
+        a = ch.process_host(np.stack([x, 2 * x]), 2)
+    assert np.max(np.abs((a[1, 1:, 0] - a[0, 1:, 0]) - 20 * np.log10(2.0))) < 1e-3
+    assert np.max(np.abs(a[1, :, 1] - a[0, :, 1])) < 1e-3
+
+
+def test_channel_swap_negates_zdr(wrp, sectors):
+    x = wrp.synth.to_planar(sectors[1])
+    y = x[[1, 0, 2]]
+    with wrp.RadarChain(0) as ch:
+        a = ch.process_host(np.stack([x, y]), 2)
+    assert np.max(np.abs(a[0, :, 1] + a[1, :, 1])) < 1e-3
+
+
+def test_doppler_phase_ramp_invariance(wrp, sectors):
+    """Multiplying every row by exp(2 pi i q j / N) circularly shifts the Doppler spectrum; the row
+    power changes only through the two clipped bins and the DC bin, i.e. marginally."""
+    x = wrp.synth.to_planar(sectors[0])
+    ramp = np.exp(2j * np.pi * 5 * np.arange(N) / N).astype(np.complex64)
+    with wrp.RadarChain(0) as ch:
+        a = ch.process_host(np.stack([x, x * ramp[None, None, :]]), 2)
+    assert np.median(np.abs(a[0, 1:, 0] - a[1, 1:, 0])) < 0.05
+
+
+def test_dc_only_input_is_noise_floor(wrp):
+    """A constant (zero-Doppler, zero-range) input is removed by the per-row mean subtraction
+    (rpv2.cu:123-130): every gate but the leakage skirt of range bin 0 drops by > 100 dB."""
+    x = np.full((1, 3, M, N), 1000 + 500j, np.complex64)
+    noisy = x + wrp.synth.to_planar(wrp.synth.make_sector_int16(M, N, 9, 0))[None]
+    with wrp.RadarChain(0) as ch:
+        a = ch.process_host(np.concatenate([x, noisy]), 2)
+    assert np.nanmax(a[0, 64:, 0]) < np.min(a[1, 64:, 0]) - 100
+
+
+def test_extreme_inputs_match_oracle(wrp, oracle):
+    """Full-scale int16 everywhere and an all-zero sector (log of zero power): same special values."""
+    full = np.full((3, M, N, 2), -16384, np.int16)
+    full[:, ::2, :, 0] = 16383
+    zero = np.zeros((3, M, N, 2), np.int16)
+    wire = np.stack([wrp.synth.to_wire(full), wrp.synth.to_wire(zero)])
+    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE) as ch:
+        out = ch.process_host(wire, 2)
+    ref = oracle.chain(wrp.synth.to_planar(full).astype(np.complex128))
+    fin = np.isfinite(ref.zdb) & (ref.zdb > ref.zdb[np.isfinite(ref.zdb)].max() - 200)
+    assert np.max(np.abs(out[0][fin, 0] - ref.zdb[fin])) <= DB_TOL
+    with np.errstate(invalid="ignore", divide="ignore"):
+        refz = oracle.chain(np.zeros((3, M, N), np.complex128))
+    assert np.all(np.isneginf(out[1][:, 0])) and np.all(np.isneginf(refz.zdb))
+    assert np.all(np.isnan(out[1][:, 1])) and np.all(np.isnan(refz.zdr))  # -inf - -inf
