@@ -286,14 +286,17 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        n_range = max(int(prof.n_range), 1)
-        sectors_per_launch = S * steps / n_range
-        range_ms = prof.ms_range / n_range
+        if int(prof.n_chain) > 0:
+            kernel, n_k, ms_k = "chain_persistent_kernel", int(prof.n_chain), prof.ms_chain
+        else:
+            kernel, n_k, ms_k = "range_fft_kernel", max(int(prof.n_range), 1), prof.ms_range
+        sectors_per_launch = S * steps / n_k
+        range_ms = ms_k / n_k
         achieved = sectors_per_launch * ALGO_BYTES_C64 / (range_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "latest_summary.json")) as f:
-                traffic = json.load(f).get("range_fft_dram_bytes_per_launch")
+                traffic = json.load(f).get(kernel + "_dram_bytes_per_launch")
         except Exception:
             pass
         chain_gbs = value / world * ALGO_BYTES_C64 / 1e9
@@ -308,12 +311,11 @@ def run_ours(args):
                        "parallelism": f"sectors sharded over {world} GPU(s), products all-gathered"},
             "iq_gbs": value * ALGO_BYTES_C64 / 1e9,
             "chain_hbm_frac": chain_gbs / peak,
-            "roofline": {"bound": "hbm", "kernel": "range_fft_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": sectors_per_launch * ALGO_BYTES_C64,
                          "mean_launch_ms": range_ms,
-                         "kernel_share_of_step": prof.ms_range / ms,
-                         "doppler_mean_launch_ms": prof.ms_doppler / max(int(prof.n_doppler), 1)},
+                         "kernel_share_of_step": ms_k / ms},
             "e2e": {"value": e2e_value, "unit": "sectors/s", "h2d_bytes_per_step": S2 * M * N * 12,
                     "d2h_bytes_per_step": S2 * M * 4, "input_fmt": "wire_i16be", "sectors_per_step_per_gpu": S2,
                     "h2d_gbs": e2e_value / world * M * N * 12 / 1e9, "api": "wrp_process_host"},

@@ -59,9 +59,11 @@ typedef enum {
 } wrp_input_fmt;
 
 typedef enum {
-    /* two fused kernels per batch (range FFT with window-on-load; Doppler FFT with
-     * mean removal, shift/clip, |.|^2, moving-average power and dB products in the
-     * epilogue).  Intermediate stages live in registers/shared memory only. */
+    /* one persistent kernel per batch: range-FFT tiles (window on load) and Doppler blocks
+     * (mean removal, shift/clip, |.|^2, moving-average power, dB products in the epilogue)
+     * interleaved on every SM; the hand-off between them lives in an L2-resident ring,
+     * every other intermediate in registers/shared memory.  (WRP_FUSED_IMPL=v1 in the
+     * environment selects the earlier two-kernel form.) */
     WRP_MODE_FUSED = 0,
     /* the reference's kernel cascade stage by stage (rpv2.cu:409-570), every stage
      * materialised in device memory so wrp_dump_stage can return 00iq..10zdr. */
@@ -120,7 +122,8 @@ typedef struct {
     double ms_range;      /* range-FFT kernel                                            */
     double ms_doppler;    /* Doppler/epilogue kernel                                     */
     double ms_staged;     /* staged cascade                                              */
-    unsigned long long n_decode, n_range, n_doppler, n_staged; /* launches measured      */
+    double ms_chain;      /* persistent fused-chain kernel (range + Doppler items)        */
+    unsigned long long n_decode, n_range, n_doppler, n_staged, n_chain; /* launches measured */
     unsigned long long sectors;                                /* sectors processed       */
 } wrp_profile;
 

@@ -70,8 +70,9 @@ class Info(C.Structure):
 class Profile(C.Structure):
     _fields_ = [
         ("ms_decode", C.c_double), ("ms_range", C.c_double), ("ms_doppler", C.c_double),
-        ("ms_staged", C.c_double), ("n_decode", C.c_ulonglong), ("n_range", C.c_ulonglong),
-        ("n_doppler", C.c_ulonglong), ("n_staged", C.c_ulonglong), ("sectors", C.c_ulonglong),
+        ("ms_staged", C.c_double), ("ms_chain", C.c_double), ("n_decode", C.c_ulonglong),
+        ("n_range", C.c_ulonglong), ("n_doppler", C.c_ulonglong), ("n_staged", C.c_ulonglong),
+        ("n_chain", C.c_ulonglong), ("sectors", C.c_ulonglong),
     ]
 
 
@@ -231,6 +232,8 @@ class RadarChain:
             host_iq = np.ascontiguousarray(host_iq)
             ptr, nbytes = host_iq.ctypes.data, host_iq.nbytes
         need = n_sectors * self.input_bytes_per_sector
+        if n_sectors < 0:
+            self._check(lib().wrp_process_host(self._h, ptr, n_sectors, None))
         if nbytes < need:
             raise ValueError(f"input holds {nbytes} bytes, {n_sectors} sectors need {need}")
         if out is None:

@@ -82,7 +82,7 @@ static void free_all(wrp_handle *h)
     wrp::StagedBuffers &b = h->staged;
     F(b.s00), F(b.s01), F(b.s02), F(b.s03), F(b.s04), F(b.s05), F(b.s06), F(b.s07), F(b.s08);
     F(b.rowsum), F(b.power), F(b.result), F(b.ham), F(b.fft_ma), F(b.tw_m), F(b.tw_n_fwd), F(b.tw_n_inv);
-    F(h->x2), F(h->decoded), F(h->power);
+    F(h->x2), F(h->decoded), F(h->power), F(h->ctrl);
     for (auto &s : h->ring) {
         if (s.pinned_in) cudaFreeHost(s.pinned_in);
         if (s.pinned_out) cudaFreeHost(s.pinned_out);
@@ -138,18 +138,38 @@ static int create_impl(wrp_handle *h)
         CK(h, upload(&h->fused.tw_b, tw_b.data(), tw_b.size() * 4));
         CK(h, wrp::fused_setup());
 
-        // chunk: sectors per kernel pair, sized so the range->Doppler hand-off
-        // (C*(M/2)*N*8 bytes per sector) stays resident in L2 between the two kernels
         const size_t inter = (size_t)C * hmn * sizeof(float2);
-        int chunk = (int)((size_t)h->l2_bytes / 3 / inter);
-        if (const char *env = getenv("WRP_CHUNK")) chunk = atoi(env);
-        if (chunk < 1) chunk = 1;
-        if (chunk > 4096) chunk = 4096;
-        h->chunk = chunk;
-        CK(h, cudaMalloc((void **)&h->x2, inter * chunk));
-        CK(h, cudaMalloc((void **)&h->power, (size_t)chunk * C * (M / 2) * sizeof(float)));
-        if (c.input_fmt == WRP_FMT_WIRE_I16BE)
-            CK(h, cudaMalloc((void **)&h->decoded, (size_t)chunk * C * mn * sizeof(float2)));
+        const char *impl = getenv("WRP_FUSED_IMPL");
+        h->persistent = !(impl && strcmp(impl, "v1") == 0) && wrp::persistent_supported(M, N);
+        if (h->persistent) {
+            // x2 hand-off = ring of sector slots that stays in L2 (ring * C*(M/2)*N*8 bytes)
+            h->x2_ring = 5;
+            if (const char *env = getenv("WRP_RING")) h->x2_ring = atoi(env);
+            if (h->x2_ring < 3) h->x2_ring = 3;
+            if (h->x2_ring > 64) h->x2_ring = 64;
+            h->smax = 1024;
+            h->chunk = h->smax;
+            CK(h, wrp::persistent_setup());
+            CK(h, cudaMalloc((void **)&h->x2, inter * h->x2_ring));
+            CK(h, cudaMalloc((void **)&h->ctrl, sizeof(int) * wrp::persistent_ctrl_ints(h->smax)));
+            CK(h, cudaMalloc((void **)&h->power, (size_t)c.max_batch * C * (M / 2) * sizeof(float)));
+            if (c.input_fmt == WRP_FMT_WIRE_I16BE) {
+                h->chunk = c.max_batch > 8 ? c.max_batch : 8; // decode scratch bounds the launch size
+                CK(h, cudaMalloc((void **)&h->decoded, (size_t)h->chunk * C * mn * sizeof(float2)));
+            }
+        } else {
+            // chunk: sectors per kernel pair, sized so the range->Doppler hand-off
+            // (C*(M/2)*N*8 bytes per sector) stays resident in L2 between the two kernels
+            int chunk = (int)((size_t)h->l2_bytes / 3 / inter);
+            if (const char *env = getenv("WRP_CHUNK")) chunk = atoi(env);
+            if (chunk < 1) chunk = 1;
+            if (chunk > 4096) chunk = 4096;
+            h->chunk = chunk;
+            CK(h, cudaMalloc((void **)&h->x2, inter * chunk));
+            CK(h, cudaMalloc((void **)&h->power, (size_t)chunk * C * (M / 2) * sizeof(float)));
+            if (c.input_fmt == WRP_FMT_WIRE_I16BE)
+                CK(h, cudaMalloc((void **)&h->decoded, (size_t)chunk * C * mn * sizeof(float2)));
+        }
     } else {
         wrp::StagedBuffers &b = h->staged;
         b.batch_capacity = c.max_batch;
@@ -251,8 +271,8 @@ int wrp_get_info(const wrp_handle *h, wrp_info *info)
     info->output_floats_per_sector = (size_t)c.n_rows_M;
     info->intermediate_bytes_per_sector = (size_t)c.n_channels * (c.n_rows_M / 2) * c.n_cols_N * 8;
     info->chunk_sectors = h->chunk;
-    info->kernels_per_chunk =
-        c.mode == WRP_MODE_FUSED ? (c.input_fmt == WRP_FMT_WIRE_I16BE ? 3 : 2) : (c.input_fmt == WRP_FMT_WIRE_I16BE ? 15 : 14);
+    const int wire = c.input_fmt == WRP_FMT_WIRE_I16BE ? 1 : 0;
+    info->kernels_per_chunk = c.mode == WRP_MODE_FUSED ? (h->persistent ? 1 : 2) + wire : 14 + wire;
     return WRP_OK;
 }
 
@@ -322,6 +342,7 @@ int wrp_profile_read(wrp_handle *h, wrp_profile *out, int reset)
         case 0: h->prof.ms_decode += ms, h->prof.n_decode++; break;
         case 1: h->prof.ms_range += ms, h->prof.n_range++; break;
         case 2: h->prof.ms_doppler += ms, h->prof.n_doppler++; break;
+        case 4: h->prof.ms_chain += ms, h->prof.n_chain++; break;
         default: h->prof.ms_staged += ms, h->prof.n_staged++; break;
         }
         h->event_pool.push_back(p.a);
@@ -360,16 +381,23 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 h->launches++;
                 planar = h->decoded;
             }
-            {
-                ProfScope ps(h, st, 1);
-                CK(h, wrp::launch_range_fft(planar, h->x2, h->fused, M, N, C, S, st));
+            if (h->persistent) {
+                ProfScope ps(h, st, 4);
+                CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->ctrl, h->smax, h->fused, M, N,
+                                             C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, st));
                 h->launches++;
-            }
-            {
-                ProfScope ps(h, st, 2);
-                CK(h, wrp::launch_doppler(h->x2, out, h->power, h->fused, M, N, C, S, c.range_res_m, c.calib,
-                                          h->host.taps_sum, st));
-                h->launches++;
+            } else {
+                {
+                    ProfScope ps(h, st, 1);
+                    CK(h, wrp::launch_range_fft(planar, h->x2, h->fused, M, N, C, S, st));
+                    h->launches++;
+                }
+                {
+                    ProfScope ps(h, st, 2);
+                    CK(h, wrp::launch_doppler(h->x2, out, h->power, h->fused, M, N, C, S, c.range_res_m, c.calib,
+                                              h->host.taps_sum, st));
+                    h->launches++;
+                }
             }
         }
         h->prof.sectors += h->profiling ? S : 0;

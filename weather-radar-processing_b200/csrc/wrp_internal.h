@@ -79,6 +79,11 @@ struct wrp_handle {
     float2 *decoded = nullptr; // [chunk][C][M][N] planar scratch for wire input
     float *power = nullptr;    // [chunk][C][M/2]
     int chunk = 1;
+    // persistent form: x2 is a ring of `ring` sector slots; ctrl holds the work/dependency counters
+    bool persistent = false;
+    int x2_ring = 5;
+    int *ctrl = nullptr;
+    int smax = 1024; // sectors per persistent launch
 
     cudaStream_t compute_stream = nullptr; // all kernels of the host path run here (owns the scratch)
     std::vector<wrp::RingSlot> ring;
@@ -109,6 +114,14 @@ cudaError_t launch_range_fft(const float2 *iq, float2 *x2, const FusedTables &t,
 cudaError_t launch_doppler(const float2 *x2, float *out, float *power, const FusedTables &t, int M, int N,
                            int C, int n_sectors, float range_res, float calib, float taps_sum,
                            cudaStream_t st);
+
+// Persistent fused chain (wrp_persistent.cu): one launch per batch of <= smax sectors.
+bool persistent_supported(int M, int N);
+cudaError_t persistent_setup();
+int persistent_ctrl_ints(int smax);
+cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int *ctrl,
+                              int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
+                              float calib, float taps_sum, int sm_count, cudaStream_t st);
 
 // Staged path (wrp_staged.cu): the reference cascade, one stage per kernel.
 // Returns the number of kernels launched through *launches.

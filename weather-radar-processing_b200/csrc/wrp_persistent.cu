@@ -1,0 +1,524 @@
+// wrp_persistent.cu — the fused chain as ONE persistent kernel per batch (sm_100a).
+//
+// Work items, handed out in queue order by an atomic counter:
+//   A(s, tile)  range tile: 8 adjacent columns x 1024 rows of one (sector, channel) plane.
+//               TMA (cp.async.bulk.tensor, one 64 KiB 4-D box) -> window on load -> radix-32 x
+//               radix-32 column FFT with an in-place shared-memory exchange -> rows k < M/2 to
+//               the x2 ring (stages 01-02; replaces __apply_hamming + the strided cuFFT plan,
+//               rpv2.cu:86-91, 318-333, 418-428).
+//   B(s, block) Doppler block: 16 rows (8 gates x hh,vv or 16 gates of vh) of the x2 ring.
+//               1-D bulk copies (cp.async.bulk, 2 x 32 KiB) -> mean removal, inverse DFT, shift,
+//               clip, |.|^2, moving-average power, ZdB/ZDR (stages 03-10; replaces rpv2.cu:93-213,
+//               434-566).  Rows are warp-private: no CTA barrier inside the transform.
+// The queue interleaves A(t) with B(t - lag), so the x2 hand-off lives in a small ring
+// (ring x 6 MiB) that never leaves L2, there is no kernel boundary between the phases, and
+// DRAM-heavy A items overlap compute-heavy B items on every SM.  Each CTA prefetches its next
+// item's bytes into the same 64 KiB buffer as soon as the current item's last shared-memory
+// read has been issued, so loads overlap the second FFT pass and the epilogue.
+// Cross-CTA ordering: per-sector completion counters (release: __threadfence + atomicAdd,
+// acquire: ld.acquire.gpu spin by the one thread that issues the dependent bulk copy).  An item
+// only ever waits for items earlier in the queue, which are held by running CTAs: no deadlock.
+#include <cuda.h>
+
+#include "wrp_fft.cuh"
+#include "wrp_internal.h"
+
+namespace wrp {
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const int *p, int target)
+{
+    while (ld_acquire(p) < target) __nanosleep(100);
+}
+
+// ---- parameters ----------------------------------------------------------------------------
+struct PersistParams {
+    const float *wrc_t;
+    const float *wd;
+    const float2 *tw_a;
+    const float2 *tw_b;
+    float2 *x2;   // ring [ring][C][M/2][N]
+    float *out;   // [S][M/2][2]
+    float *power; // optional [S][C][M/2]
+    int *ctrl;    // [0] work counter; a_done at CTRL_A; b_done at CTRL_A + smax
+    int S, C, N, half_m;
+    int ring, lag;
+    int tiles_a, blocks_b, pair_blocks;
+    int n1, n2, n3, b3_first; // queue regions (see decode_item)
+    int total_items;
+    int smax;
+    float range_res, calib, taps_sum;
+};
+constexpr int CTRL_A = 32;
+constexpr int TILE_BYTES = 65536;
+
+struct Item {
+    int kind; // 0 = range tile, 1 = Doppler block
+    int sector;
+    int sub;
+};
+
+// queue: n1 steps of [A]; n2 steps of [A, B]; n3 steps of [B]
+__device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
+{
+    Item it;
+    const int TA = p.tiles_a, TB = p.blocks_b;
+    if (idx < p.n1 * TA) {
+        it.kind = 0;
+        it.sector = idx / TA;
+        it.sub = idx - it.sector * TA;
+        return it;
+    }
+    idx -= p.n1 * TA;
+    const int per = TA + TB;
+    if (idx < p.n2 * per) {
+        const int t = idx / per, r = idx - t * per;
+        if (r < TA) {
+            it.kind = 0;
+            it.sector = p.n1 + t;
+            it.sub = r;
+        } else {
+            it.kind = 1;
+            it.sector = t;
+            it.sub = r - TA;
+        }
+        return it;
+    }
+    idx -= p.n2 * per;
+    it.kind = 1;
+    const int t = idx / TB;
+    it.sector = p.b3_first + t;
+    it.sub = idx - t * TB;
+    return it;
+}
+
+// thread 0: launch the item's async copy into `buf` once its dependency is met.  With
+// blocking == false the dependency is only probed (a CTA must never spin while it still holds
+// an unfinished item: the item it waits for could be its own); returns whether the copy was
+// issued.
+__device__ __forceinline__ bool issue_load(const Item &it, const PersistParams &p, const CUtensorMap *tmap,
+                                           uint8_t *buf, uint64_t *bar, bool blocking)
+{
+    if (it.kind == 0) {
+        // WAR on the ring slot this tile will write: the Doppler blocks of sector - ring must
+        // have pulled their rows already
+        if (it.sector >= p.ring) {
+            const int *dep = p.ctrl + CTRL_A + p.smax + (it.sector - p.ring);
+            if (blocking)
+                spin_until(dep, p.blocks_b);
+            else if (ld_acquire(dep) < p.blocks_b)
+                return false;
+        }
+        const int tiles_per_plane = p.N / 8;
+        const int ch = it.sub / tiles_per_plane, tile = it.sub - ch * tiles_per_plane;
+        fence_proxy_async();
+        mbar_expect_tx(bar, TILE_BYTES);
+        tma_load_4d(buf, tmap, tile * 16, 0, 0, it.sector * p.C + ch, bar);
+    } else {
+        const int *dep = p.ctrl + CTRL_A + it.sector;
+        if (blocking)
+            spin_until(dep, p.tiles_a * 8);
+        else if (ld_acquire(dep) < p.tiles_a * 8)
+            return false;
+        fence_proxy_async();
+        mbar_expect_tx(bar, TILE_BYTES);
+        const int slot = it.sector % p.ring;
+        const size_t row_bytes = (size_t)p.N * sizeof(float2);
+        const int rows = TILE_BYTES / (int)row_bytes; // 16 (N=512) or 8 (N=1024)
+        if (it.sub < p.pair_blocks) {
+            const int g0 = it.sub * (rows / 2);
+            const uint8_t *hh = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
+            const uint8_t *vv = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 1) * p.half_m + g0) * row_bytes;
+            bulk_load(buf, hh, TILE_BYTES / 2, bar);
+            bulk_load(buf + TILE_BYTES / 2, vv, TILE_BYTES / 2, bar);
+        } else {
+            const int g0 = (it.sub - p.pair_blocks) * rows;
+            const int ch = p.C == 1 ? 0 : 2;
+            const uint8_t *src = (const uint8_t *)p.x2 + (((size_t)slot * p.C + ch) * p.half_m + g0) * row_bytes;
+            bulk_load(buf, src, TILE_BYTES, bar);
+        }
+    }
+    return true;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+template <int R1B> // Doppler length N = 32 * R1B
+__global__ void __launch_bounds__(256, 2)
+    chain_persistent_kernel(const __grid_constant__ CUtensorMap tmap_in, const PersistParams p)
+{
+    constexpr int M = 1024, R = 32; // range FFT 32 x 32
+    constexpr int N = 32 * R1B;
+    constexpr int ROWS_B = TILE_BYTES / (N * 8);   // Doppler rows per block
+    constexpr int RPW = ROWS_B / 8;                // rows per warp
+    extern __shared__ __align__(1024) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int s_next[2];
+    __shared__ float p_row[ROWS_B];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        const int first = atomicAdd(p.ctrl, 1);
+        s_next[0] = first < p.total_items ? first : -1;
+    }
+    __syncthreads();
+    int cur = s_next[0];
+    if (tid == 0 && cur >= 0) issue_load(decode_item(cur, p), p, &tmap_in, tile, &mbar, true);
+    uint32_t phase = 0;
+    int it_count = 0;
+
+    while (cur >= 0) {
+        const Item it = decode_item(cur, p);
+        const int nslot = (it_count + 1) & 1;
+        ++it_count;
+        int nxt;
+        bool issued = true; // meaningful on thread 0 only
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+
+        if (it.kind == 0) {
+            // ================= range tile =================
+            const int c = tid & 7, b = tid >> 3;
+            const int tiles_per_plane = p.N / 8;
+            const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * 8 + c;
+            float2 v[R];
+            {
+                const uint8_t *src = tile + b * 64 + c * 8;
+                static_for<R>([&](auto ai) {
+                    constexpr int a = decltype(ai)::value;
+                    v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * 64));
+                });
+                const float wdj = __ldg(p.wd + col);
+                const float4 *w4 = reinterpret_cast<const float4 *>(p.wrc_t) + b * (R / 4);
+                static_for<R / 4>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = __ldg(w4 + q);
+                    const float w0 = w.x * wdj, w1 = w.y * wdj, w2 = w.z * wdj, w3 = w.w * wdj;
+                    v[brev<R>(4 * q + 0)].x *= w0;
+                    v[brev<R>(4 * q + 0)].y *= w0;
+                    v[brev<R>(4 * q + 1)].x *= w1;
+                    v[brev<R>(4 * q + 1)].y *= w1;
+                    v[brev<R>(4 * q + 2)].x *= w2;
+                    v[brev<R>(4 * q + 2)].y *= w2;
+                    v[brev<R>(4 * q + 3)].x *= w3;
+                    v[brev<R>(4 * q + 3)].y *= w3;
+                });
+            }
+            fft_dit<R, -1>(v);
+            __syncwarp();
+            {
+                // Z[ka][b] goes to row 32 ka + (b ^ (ka & 1)): same 4-row x 64 B footprint per warp
+                // (in place), and pass 2's two ka per half-warp fall into different 64 B halves
+                const float4 *t4 = reinterpret_cast<const float4 *>(p.tw_a) + b * (R / 2);
+                uint8_t *d_even = tile + b * 64 + c * 8;
+                uint8_t *d_odd = tile + (b ^ 1) * 64 + c * 8;
+                static_for<R / 2>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = __ldg(t4 + q);
+                    const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                    const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                    *reinterpret_cast<float2 *>(d_even + (2 * q) * (R * 64)) = y0;
+                    *reinterpret_cast<float2 *>(d_odd + (2 * q + 1) * (R * 64)) = y1;
+                });
+            }
+            __syncthreads();
+            const int ka = b;
+            {
+                const int par = (ka & 1) * 64;
+                const uint8_t *s_even = tile + ka * (R * 64) + c * 8 + par; // even b: row b + (ka&1)
+                const uint8_t *s_odd = tile + ka * (R * 64) + c * 8 - par;  // odd b:  row b - (ka&1)
+                static_for<R>([&](auto bi) {
+                    constexpr int bb = decltype(bi)::value;
+                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(((bb & 1) ? s_odd : s_even) + bb * 64);
+                });
+            }
+            if (tid == 0) {
+                const int n = atomicAdd(p.ctrl, 1);
+                s_next[nslot] = n < p.total_items ? n : -1;
+            }
+            __syncthreads(); // every shared-memory read of this item is done; s_next is visible
+            nxt = s_next[nslot];
+            if (tid == 0 && nxt >= 0) issued = issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, false);
+            fft_dit<R, -1>(v);
+            {
+                float2 *out = p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m) * (size_t)p.N + col;
+                static_for<R / 2>([&](auto ki) { // rows k = ka + 32 kb < M/2
+                    constexpr int kb = decltype(ki)::value;
+                    out[(size_t)(ka + R * kb) * p.N] = v[kb];
+                });
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.ctrl + CTRL_A + it.sector, 1);
+        } else {
+            // ================= Doppler block =================
+            if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1); // ring rows are in smem now
+            const bool pair = it.sub < p.pair_blocks;
+            // warp w owns rows w and (RPW == 2) ROWS_B/2 + w: (hh, vv) of one gate in a pair block
+            {
+                float2 tw[R1B];
+                const float4 *t4 = reinterpret_cast<const float4 *>(p.tw_b) + lane * (R1B / 2);
+                static_for<R1B / 2>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = __ldg(t4 + q);
+                    tw[2 * q] = make_float2(w.x, w.y);
+                    tw[2 * q + 1] = make_float2(w.z, w.w);
+                });
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) {
+                    uint8_t *row = tile + (size_t)(warp + rr * (ROWS_B / 2)) * (N * 8);
+                    float2 v[R1B];
+                    static_for<R1B>([&](auto ai) {
+                        constexpr int a = decltype(ai)::value;
+                        v[brev<R1B>(a)] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
+                    });
+                    fft_dit<R1B, +1>(v);
+                    // mean removal (rpv2.cu:93-130): only the a-sum (ka = 0) carries the row mean
+                    float sx = v[0].x, sy = v[0].y;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                    }
+                    v[0].x -= sx * (1.f / 32.f);
+                    v[0].y -= sy * (1.f / 32.f);
+                    __syncwarp();
+                    // Z_l[ka] -> float2 index 32 ka + (l ^ ((ka & 7) << 1)): 16-byte chunks of group ka
+                    // are XOR-swizzled so pass 2's 128-bit reads are conflict-free
+                    static_for<R1B>([&](auto ki) {
+                        constexpr int ka = decltype(ki)::value;
+                        const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
+                        *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
+                    });
+                }
+            }
+            __syncwarp();
+            float2 u[32];
+            const int rsel = RPW == 2 ? (lane >> 4) : 0;
+            const int ka = RPW == 2 ? (lane & 15) : lane;
+            const int my_row = warp + rsel * (ROWS_B / 2);
+            {
+                const uint8_t *grp = tile + (size_t)my_row * (N * 8) + ka * 256;
+                const int sw = (ka & 7) * 16;
+                static_for<16>([&](auto ci) {
+                    constexpr int cc = decltype(ci)::value;
+                    const float4 q = *reinterpret_cast<const float4 *>(grp + ((cc * 16) ^ sw));
+                    u[brev<32>(2 * cc)] = make_float2(q.x, q.y);
+                    u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
+                });
+            }
+            if (tid == 0) {
+                const int n = atomicAdd(p.ctrl, 1);
+                s_next[nslot] = n < p.total_items ? n : -1;
+            }
+            __syncthreads();
+            nxt = s_next[nslot];
+            if (tid == 0 && nxt >= 0) issued = issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, false);
+            fft_dit<32, +1>(u);
+            // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
+            // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
+            float pw = 0.f;
+            static_for<32>([&](auto ki) {
+                constexpr int kb = decltype(ki)::value;
+                const float e = fmaf(u[kb].x, u[kb].x, u[kb].y * u[kb].y);
+                if (kb == 15) {
+                    if (ka < R1B - 2) pw += e;
+                } else {
+                    pw += e;
+                }
+            });
+#pragma unroll
+            for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+            pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
+            // (channel, gate) of my_row
+            const int g0 = pair ? it.sub * (ROWS_B / 2) : (it.sub - p.pair_blocks) * ROWS_B;
+            const int chn = pair ? (my_row >= ROWS_B / 2 ? 1 : 0) : (p.C == 1 ? 0 : 2);
+            const int gate = pair ? g0 + (my_row % (ROWS_B / 2)) : g0 + my_row;
+            if (p.power && ka == 0) p.power[((size_t)it.sector * p.C + chn) * p.half_m + gate] = pw;
+            if constexpr (RPW == 2) {
+                const float other = __shfl_xor_sync(0xffffffffu, pw, 16);
+                if (pair && lane == 0) {
+                    const float rg = (float)gate * p.range_res;
+                    const float z = rg * rg * p.calib * pw;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + gate] =
+                        make_float2(10.f * log10f(z), 10.f * (log10f(pw) - log10f(other)));
+                } else if (!pair && p.C == 1 && ka == 0) {
+                    const float rg = (float)gate * p.range_res;
+                    const float z = rg * rg * p.calib * pw;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + gate] =
+                        make_float2(10.f * log10f(z), 0.f);
+                }
+            } else {
+                if (ka == 0) p_row[my_row] = pw;
+                __syncthreads();
+                if (pair && tid < ROWS_B / 2) {
+                    const int g = g0 + tid;
+                    const float p_hh = p_row[tid], p_vv = p_row[ROWS_B / 2 + tid];
+                    const float rg = (float)g * p.range_res;
+                    const float z = rg * rg * p.calib * p_hh;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + g] =
+                        make_float2(10.f * log10f(z), 10.f * (log10f(p_hh) - log10f(p_vv)));
+                } else if (!pair && p.C == 1 && tid < ROWS_B) {
+                    const int g = g0 + tid;
+                    const float rg = (float)g * p.range_res;
+                    const float z = rg * rg * p.calib * p_row[tid];
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + g] =
+                        make_float2(10.f * log10f(z), 0.f);
+                }
+                __syncthreads();
+            }
+        }
+        // the probe found the next item's dependency unmet: this CTA's own item is signalled
+        // (or about to be, by its other warps), so a blocking wait is safe now
+        if (tid == 0 && nxt >= 0 && !issued) issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, true);
+        cur = nxt;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool persistent_supported(int M, int N) { return M == 1024 && (N == 512 || N == 1024); }
+int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
+
+cudaError_t persistent_setup()
+{
+    cudaError_t e = cudaFuncSetAttribute(chain_persistent_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TILE_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(chain_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TILE_BYTES);
+}
+
+// One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
+cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int *ctrl,
+                              int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
+                              float calib, float taps_sum, int sm_count, cudaStream_t st)
+{
+    if (n_sectors == 0) return cudaSuccess;
+    if (!persistent_supported(M, N) || n_sectors > smax) return cudaErrorInvalidValue;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return cudaErrorNotSupported;
+
+    // input as a 4-D tensor (2N floats, 32 rows b, 32 row-groups a, planes); box = one range tile
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)2 * N, 32, 32, (cuuint64_t)C * n_sectors};
+    const cuuint64_t gstr[3] = {(cuuint64_t)N * 8, (cuuint64_t)32 * N * 8, (cuuint64_t)M * N * 8};
+    const cuuint32_t box[4] = {16, 32, 32, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)iq, gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+
+    PersistParams p{};
+    p.wrc_t = t.wrc_t;
+    p.wd = t.wd;
+    p.tw_a = t.tw_a;
+    p.tw_b = t.tw_b;
+    p.x2 = x2_ring;
+    p.out = out;
+    p.power = power;
+    p.ctrl = ctrl;
+    p.S = n_sectors;
+    p.C = C;
+    p.N = N;
+    p.half_m = M / 2;
+    p.ring = ring;
+    p.lag = ring >= 5 ? 2 : 1;
+    const int rows_b = TILE_BYTES / (N * 8);
+    p.tiles_a = (N / 8) * C;
+    p.pair_blocks = C >= 2 ? (M / 2) / (rows_b / 2) : 0;
+    p.blocks_b = p.pair_blocks + ((C & 1) ? (M / 2) / rows_b : 0);
+    const int L = p.lag, S = n_sectors;
+    p.n1 = S < L ? S : L;
+    p.n2 = S > L ? S - L : 0;
+    p.n3 = S < L ? S : L;
+    p.b3_first = S > L ? S - L : 0;
+    p.total_items = S * (p.tiles_a + p.blocks_b);
+    p.smax = smax;
+    p.range_res = range_res;
+    p.calib = calib;
+    p.taps_sum = taps_sum;
+
+    cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
+    if (e != cudaSuccess) return e;
+    int grid = 2 * sm_count;
+    if (grid > p.total_items) grid = p.total_items;
+    if (N == 512)
+        chain_persistent_kernel<16><<<grid, 256, TILE_BYTES, st>>>(tmap, p);
+    else
+        chain_persistent_kernel<32><<<grid, 256, TILE_BYTES, st>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+} // namespace wrp
