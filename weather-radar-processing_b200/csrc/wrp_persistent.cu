@@ -18,8 +18,6 @@
 // Cross-CTA ordering: per-sector completion counters (release: __threadfence + atomicAdd,
 // acquire: ld.acquire.gpu spin by the one thread that issues the dependent bulk copy).  An item
 // only ever waits for items earlier in the queue, which are held by running CTAs: no deadlock.
-#include <cuda.h>
-
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
 
@@ -58,14 +56,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
-                                            uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-                 "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -73,11 +63,26 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// release-add: orders this thread's prior writes and, through the preceding CTA barrier, the
+// whole CTA's (cumulativity); no L1 invalidation, unlike __threadfence()
+__device__ __forceinline__ void red_release_add(int *p)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ void spin_until(const int *p, int target)
 {
@@ -90,6 +95,7 @@ struct PersistParams {
     const float *wd;
     const float2 *tw_a;
     const float2 *tw_b;
+    const float2 *iq; // input [S][C][M][N]
     float2 *x2;   // ring [ring][C][M/2][N]
     float *out;   // [S][M/2][2]
     float *power; // optional [S][C][M/2]
@@ -104,6 +110,25 @@ struct PersistParams {
 };
 constexpr int CTRL_A = 32;
 constexpr int TILE_BYTES = 65536;
+// shared-memory copies of the small tables (no L1 dependence: the acquire loads of the
+// dependency counters invalidate L1)
+// rows are padded by 16 B so that the 128-bit reads of lanes holding different rows hit
+// different banks
+constexpr int WRC_ROW = 32 * 4 + 16;   // wr(i)*c transposed [32][32] float
+constexpr int TWA_ROW = 32 * 8 + 16;   // range inter-pass twiddles [32][32] float2
+constexpr int TAB_WRC = 32 * WRC_ROW;
+constexpr int TAB_TWA = 32 * TWA_ROW;
+template <int R1B> struct Tables {
+    static constexpr int N = 32 * R1B;
+    static constexpr int TWB_ROW = R1B * 8 + 16; // Doppler inter-pass twiddles [32][R1B] float2
+    static constexpr int WD = N * 4;             // Doppler window
+    static constexpr int TWB = 32 * TWB_ROW;
+    static constexpr int OFF_WRC = TILE_BYTES;
+    static constexpr int OFF_TWA = OFF_WRC + TAB_WRC;
+    static constexpr int OFF_TWB = OFF_TWA + TAB_TWA;
+    static constexpr int OFF_WD = OFF_TWB + TWB;
+    static constexpr int SMEM = OFF_WD + WD;
+};
 
 struct Item {
     int kind; // 0 = range tile, 1 = Doppler block
@@ -145,79 +170,121 @@ __device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
     return it;
 }
 
-// thread 0: launch the item's async copy into `buf` once its dependency is met.  With
-// blocking == false the dependency is only probed (a CTA must never spin while it still holds
-// an unfinished item: the item it waits for could be its own); returns whether the copy was
-// issued.
-__device__ __forceinline__ bool issue_load(const Item &it, const PersistParams &p, const CUtensorMap *tmap,
-                                           uint8_t *buf, uint64_t *bar, bool blocking)
+// dependency of an item: the counter it must see reach `target` before its copy may start
+//   range tile of sector s >= ring: WAR on ring slot — the Doppler blocks of sector s - ring must
+//                                   have pulled their rows;
+//   Doppler block of sector s:      every range tile of sector s has been written.
+__device__ __forceinline__ const int *item_dep(const Item &it, const PersistParams &p, int &target)
 {
     if (it.kind == 0) {
-        // WAR on the ring slot this tile will write: the Doppler blocks of sector - ring must
-        // have pulled their rows already
-        if (it.sector >= p.ring) {
-            const int *dep = p.ctrl + CTRL_A + p.smax + (it.sector - p.ring);
-            if (blocking)
-                spin_until(dep, p.blocks_b);
-            else if (ld_acquire(dep) < p.blocks_b)
-                return false;
-        }
-        const int tiles_per_plane = p.N / 8;
-        const int ch = it.sub / tiles_per_plane, tile = it.sub - ch * tiles_per_plane;
-        fence_proxy_async();
-        mbar_expect_tx(bar, TILE_BYTES);
-        tma_load_4d(buf, tmap, tile * 16, 0, 0, it.sector * p.C + ch, bar);
-    } else {
-        const int *dep = p.ctrl + CTRL_A + it.sector;
-        if (blocking)
-            spin_until(dep, p.tiles_a * 8);
-        else if (ld_acquire(dep) < p.tiles_a * 8)
-            return false;
-        fence_proxy_async();
-        mbar_expect_tx(bar, TILE_BYTES);
-        const int slot = it.sector % p.ring;
-        const size_t row_bytes = (size_t)p.N * sizeof(float2);
-        const int rows = TILE_BYTES / (int)row_bytes; // 16 (N=512) or 8 (N=1024)
-        if (it.sub < p.pair_blocks) {
-            const int g0 = it.sub * (rows / 2);
-            const uint8_t *hh = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
-            const uint8_t *vv = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 1) * p.half_m + g0) * row_bytes;
-            bulk_load(buf, hh, TILE_BYTES / 2, bar);
-            bulk_load(buf + TILE_BYTES / 2, vv, TILE_BYTES / 2, bar);
-        } else {
-            const int g0 = (it.sub - p.pair_blocks) * rows;
-            const int ch = p.C == 1 ? 0 : 2;
-            const uint8_t *src = (const uint8_t *)p.x2 + (((size_t)slot * p.C + ch) * p.half_m + g0) * row_bytes;
-            bulk_load(buf, src, TILE_BYTES, bar);
-        }
+        target = p.blocks_b;
+        return it.sector >= p.ring ? p.ctrl + CTRL_A + p.smax + (it.sector - p.ring) : nullptr;
     }
-    return true;
+    target = p.tiles_a;
+    return p.ctrl + CTRL_A + it.sector;
+}
+__device__ __forceinline__ bool dep_ready(const Item &it, const PersistParams &p)
+{
+    int target;
+    const int *dep = item_dep(it, p, target);
+    return dep == nullptr || ld_acquire(dep) >= target;
+}
+__device__ __forceinline__ void dep_wait(const Item &it, const PersistParams &p)
+{
+    int target;
+    const int *dep = item_dep(it, p, target);
+    if (dep) spin_until(dep, target);
+}
+
+// Doppler block (thread 0): two 32 KiB (or one 64 KiB) contiguous bulk copies from the x2 ring
+__device__ __forceinline__ void issue_load_b(const Item &it, const PersistParams &p, uint8_t *buf, uint64_t *bar)
+{
+    fence_proxy_async();
+    mbar_expect_tx(bar, TILE_BYTES);
+    const int slot = it.sector % p.ring;
+    const size_t row_bytes = (size_t)p.N * sizeof(float2);
+    const int rows = TILE_BYTES / (int)row_bytes; // 16 (N=512) or 8 (N=1024)
+    if (it.sub < p.pair_blocks) {
+        const int g0 = it.sub * (rows / 2);
+        const uint8_t *hh = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
+        const uint8_t *vv = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 1) * p.half_m + g0) * row_bytes;
+        bulk_load(buf, hh, TILE_BYTES / 2, bar);
+        bulk_load(buf + TILE_BYTES / 2, vv, TILE_BYTES / 2, bar);
+    } else {
+        const int g0 = (it.sub - p.pair_blocks) * rows;
+        const int ch = p.C == 1 ? 0 : 2;
+        const uint8_t *src = (const uint8_t *)p.x2 + (((size_t)slot * p.C + ch) * p.half_m + g0) * row_bytes;
+        bulk_load(buf, src, TILE_BYTES, bar);
+    }
+}
+
+// Range tile (all 256 threads): 1024 rows x 64 B, 16 B per cp.async (a warp covers 8 rows x 64 B).
+// A 4-D TMA box was tried first: one 64 B row per request throttles the TMA unit (~5 us per tile).
+template <int N>
+__device__ __forceinline__ void issue_load_a(const Item &it, const PersistParams &p, uint8_t *buf, uint64_t *bar,
+                                             int tid)
+{
+    constexpr int tiles_per_plane = N / 8;
+    const int ch = it.sub / tiles_per_plane, tile = it.sub - ch * tiles_per_plane;
+    const uint8_t *src = (const uint8_t *)p.iq + ((size_t)(it.sector * p.C + ch) * 1024 + (tid >> 2)) * (N * 8) +
+                         tile * 64 + (tid & 3) * 16;
+    uint8_t *dst = buf + tid * 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 4096, src + (size_t)k * 64 * (N * 8));
+    cp_async_arrive(bar);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
 template <int R1B> // Doppler length N = 32 * R1B
 __global__ void __launch_bounds__(256, 2)
-    chain_persistent_kernel(const __grid_constant__ CUtensorMap tmap_in, const PersistParams p)
+    chain_persistent_kernel(const PersistParams p)
 {
-    constexpr int M = 1024, R = 32; // range FFT 32 x 32
+    constexpr int R = 32; // range FFT 32 x 32 (M = 1024)
     constexpr int N = 32 * R1B;
     constexpr int ROWS_B = TILE_BYTES / (N * 8);   // Doppler rows per block
     constexpr int RPW = ROWS_B / 8;                // rows per warp
+    using Tab = Tables<R1B>;
     extern __shared__ __align__(1024) uint8_t tile[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ int s_next[2];
+    __shared__ __align__(8) uint64_t mbar_a, mbar_b; // range tiles (256 cp.async arrivals) / Doppler blocks (tx bytes)
+    __shared__ int s_next[2], s_ready[2];
     __shared__ float p_row[ROWS_B];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        // copy the tables into (row-padded) shared memory, 16 B per step
+        auto copy_rows = [&](int off, const void *src, int rows, int row_bytes, int row_pitch) {
+            const int per_row = row_bytes / 16;
+            for (int i = tid; i < rows * per_row; i += 256) {
+                const int r = i / per_row, q = i - r * per_row;
+                *reinterpret_cast<float4 *>(tile + off + r * row_pitch + q * 16) =
+                    __ldg(reinterpret_cast<const float4 *>(src) + i);
+            }
+        };
+        copy_rows(Tab::OFF_WRC, p.wrc_t, 32, 32 * 4, WRC_ROW);
+        copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
+        copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
+        copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
+    }
+    int pending = -1; // sector whose range tile this CTA finished but has not signalled yet
     if (tid == 0) {
-        mbar_init(&mbar, 1);
+        mbar_init(&mbar_a, 256);
+        mbar_init(&mbar_b, 1);
         const int first = atomicAdd(p.ctrl, 1);
         s_next[0] = first < p.total_items ? first : -1;
     }
     __syncthreads();
     int cur = s_next[0];
-    if (tid == 0 && cur >= 0) issue_load(decode_item(cur, p), p, &tmap_in, tile, &mbar, true);
-    uint32_t phase = 0;
+    if (cur >= 0) {
+        const Item first = decode_item(cur, p);
+        if (tid == 0) dep_wait(first, p);
+        if (first.kind == 0) {
+            __syncthreads();
+            issue_load_a<N>(first, p, tile, &mbar_a, tid);
+        } else if (tid == 0) {
+            issue_load_b(first, p, tile, &mbar_b);
+        }
+    }
+    uint32_t phase_a = 0, phase_b = 0;
     int it_count = 0;
 
     while (cur >= 0) {
@@ -225,14 +292,19 @@ __global__ void __launch_bounds__(256, 2)
         const int nslot = (it_count + 1) & 1;
         ++it_count;
         int nxt;
-        bool issued = true; // meaningful on thread 0 only
-        mbar_wait(&mbar, phase);
-        phase ^= 1;
+        bool ready; // next item's dependency was met when probed (CTA-uniform)
+        if (it.kind == 0) {
+            mbar_wait(&mbar_a, phase_a);
+            phase_a ^= 1;
+        } else {
+            mbar_wait(&mbar_b, phase_b);
+            phase_b ^= 1;
+        }
 
         if (it.kind == 0) {
             // ================= range tile =================
             const int c = tid & 7, b = tid >> 3;
-            const int tiles_per_plane = p.N / 8;
+            constexpr int tiles_per_plane = N / 8;
             const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * 8 + c;
             float2 v[R];
             {
@@ -241,11 +313,11 @@ __global__ void __launch_bounds__(256, 2)
                     constexpr int a = decltype(ai)::value;
                     v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * 64));
                 });
-                const float wdj = __ldg(p.wd + col);
-                const float4 *w4 = reinterpret_cast<const float4 *>(p.wrc_t) + b * (R / 4);
+                const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
+                const float4 *w4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_WRC + b * WRC_ROW);
                 static_for<R / 4>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = __ldg(w4 + q);
+                    const float4 w = w4[q];
                     const float w0 = w.x * wdj, w1 = w.y * wdj, w2 = w.z * wdj, w3 = w.w * wdj;
                     v[brev<R>(4 * q + 0)].x *= w0;
                     v[brev<R>(4 * q + 0)].y *= w0;
@@ -262,12 +334,12 @@ __global__ void __launch_bounds__(256, 2)
             {
                 // Z[ka][b] goes to row 32 ka + (b ^ (ka & 1)): same 4-row x 64 B footprint per warp
                 // (in place), and pass 2's two ka per half-warp fall into different 64 B halves
-                const float4 *t4 = reinterpret_cast<const float4 *>(p.tw_a) + b * (R / 2);
+                const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWA + b * TWA_ROW);
                 uint8_t *d_even = tile + b * 64 + c * 8;
                 uint8_t *d_odd = tile + (b ^ 1) * 64 + c * 8;
                 static_for<R / 2>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = __ldg(t4 + q);
+                    const float4 w = t4[q];
                     const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
                     const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
                     *reinterpret_cast<float2 *>(d_even + (2 * q) * (R * 64)) = y0;
@@ -275,6 +347,8 @@ __global__ void __launch_bounds__(256, 2)
                 });
             }
             __syncthreads();
+            if (tid == 0 && pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
+            pending = -1;
             const int ka = b;
             {
                 const int par = (ka & 1) * 64;
@@ -288,21 +362,29 @@ __global__ void __launch_bounds__(256, 2)
             if (tid == 0) {
                 const int n = atomicAdd(p.ctrl, 1);
                 s_next[nslot] = n < p.total_items ? n : -1;
+                s_ready[nslot] = n < p.total_items ? (int)dep_ready(decode_item(n, p), p) : 1;
             }
             __syncthreads(); // every shared-memory read of this item is done; s_next is visible
             nxt = s_next[nslot];
-            if (tid == 0 && nxt >= 0) issued = issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, false);
+            ready = s_ready[nslot] != 0;
+            if (nxt >= 0 && ready) {
+                const Item nit = decode_item(nxt, p);
+                if (nit.kind == 0)
+                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                else if (tid == 0)
+                    issue_load_b(nit, p, tile, &mbar_b);
+            }
             fft_dit<R, -1>(v);
             {
-                float2 *out = p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m) * (size_t)p.N + col;
+                float2 *out = p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m + ka) * (size_t)N + col;
                 static_for<R / 2>([&](auto ki) { // rows k = ka + 32 kb < M/2
                     constexpr int kb = decltype(ki)::value;
-                    out[(size_t)(ka + R * kb) * p.N] = v[kb];
+                    out[(size_t)(R * kb) * N] = v[kb];
                 });
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicAdd(p.ctrl + CTRL_A + it.sector, 1);
+            // completion of this tile is signalled (release) by thread 0 after the next CTA
+            // barrier, when these stores have long drained: no fence stall here
+            pending = it.sector;
         } else {
             // ================= Doppler block =================
             if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1); // ring rows are in smem now
@@ -310,10 +392,10 @@ __global__ void __launch_bounds__(256, 2)
             // warp w owns rows w and (RPW == 2) ROWS_B/2 + w: (hh, vv) of one gate in a pair block
             {
                 float2 tw[R1B];
-                const float4 *t4 = reinterpret_cast<const float4 *>(p.tw_b) + lane * (R1B / 2);
+                const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWB + lane * Tab::TWB_ROW);
                 static_for<R1B / 2>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = __ldg(t4 + q);
+                    const float4 w = t4[q];
                     tw[2 * q] = make_float2(w.x, w.y);
                     tw[2 * q + 1] = make_float2(w.z, w.w);
                 });
@@ -363,10 +445,20 @@ __global__ void __launch_bounds__(256, 2)
             if (tid == 0) {
                 const int n = atomicAdd(p.ctrl, 1);
                 s_next[nslot] = n < p.total_items ? n : -1;
+                s_ready[nslot] = n < p.total_items ? (int)dep_ready(decode_item(n, p), p) : 1;
             }
             __syncthreads();
+            if (tid == 0 && pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
+            pending = -1;
             nxt = s_next[nslot];
-            if (tid == 0 && nxt >= 0) issued = issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, false);
+            ready = s_ready[nslot] != 0;
+            if (nxt >= 0 && ready) {
+                const Item nit = decode_item(nxt, p);
+                if (nit.kind == 0)
+                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                else if (tid == 0)
+                    issue_load_b(nit, p, tile, &mbar_b);
+            }
             fft_dit<32, +1>(u);
             // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
             // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
@@ -423,40 +515,40 @@ __global__ void __launch_bounds__(256, 2)
         }
         // the probe found the next item's dependency unmet: this CTA's own item is signalled
         // (or about to be, by its other warps), so a blocking wait is safe now
-        if (tid == 0 && nxt >= 0 && !issued) issue_load(decode_item(nxt, p), p, &tmap_in, tile, &mbar, true);
+        if (nxt < 0 || !ready) {
+            // leaving the loop, or about to block on a dependency: publish the pending tile first
+            // (the item waited for may be this CTA's own).  nxt and ready are CTA-uniform.
+            if (pending >= 0) {
+                __syncthreads();
+                if (tid == 0) red_release_add(p.ctrl + CTRL_A + pending);
+                pending = -1;
+            }
+            if (nxt >= 0) {
+                const Item nit = decode_item(nxt, p);
+                if (tid == 0) dep_wait(nit, p);
+                if (nit.kind == 0) {
+                    __syncthreads();
+                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                } else if (tid == 0) {
+                    issue_load_b(nit, p, tile, &mbar_b);
+                }
+            }
+        }
         cur = nxt;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 bool persistent_supported(int M, int N) { return M == 1024 && (N == 512 || N == 1024); }
 int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
 
 cudaError_t persistent_setup()
 {
     cudaError_t e = cudaFuncSetAttribute(chain_persistent_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TILE_BYTES);
+                                         Tables<16>::SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(chain_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TILE_BYTES);
+                                Tables<32>::SMEM);
 }
 
 // One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
@@ -466,25 +558,12 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
 {
     if (n_sectors == 0) return cudaSuccess;
     if (!persistent_supported(M, N) || n_sectors > smax) return cudaErrorInvalidValue;
-    EncodeTiledFn encode = get_encode();
-    if (!encode) return cudaErrorNotSupported;
-
-    // input as a 4-D tensor (2N floats, 32 rows b, 32 row-groups a, planes); box = one range tile
-    CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {(cuuint64_t)2 * N, 32, 32, (cuuint64_t)C * n_sectors};
-    const cuuint64_t gstr[3] = {(cuuint64_t)N * 8, (cuuint64_t)32 * N * 8, (cuuint64_t)M * N * 8};
-    const cuuint32_t box[4] = {16, 32, 32, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)iq, gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return cudaErrorInvalidValue;
-
     PersistParams p{};
     p.wrc_t = t.wrc_t;
     p.wd = t.wd;
     p.tw_a = t.tw_a;
     p.tw_b = t.tw_b;
+    p.iq = iq;
     p.x2 = x2_ring;
     p.out = out;
     p.power = power;
@@ -515,9 +594,9 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     int grid = 2 * sm_count;
     if (grid > p.total_items) grid = p.total_items;
     if (N == 512)
-        chain_persistent_kernel<16><<<grid, 256, TILE_BYTES, st>>>(tmap, p);
+        chain_persistent_kernel<16><<<grid, 256, Tables<16>::SMEM, st>>>(p);
     else
-        chain_persistent_kernel<32><<<grid, 256, TILE_BYTES, st>>>(tmap, p);
+        chain_persistent_kernel<32><<<grid, 256, Tables<32>::SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
