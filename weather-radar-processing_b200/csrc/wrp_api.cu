@@ -143,9 +143,10 @@ static int create_impl(wrp_handle *h)
         h->persistent = !(impl && strcmp(impl, "v1") == 0) && wrp::persistent_supported(M, N);
         if (h->persistent) {
             // x2 hand-off = ring of sector slots that stays in L2 (ring * C*(M/2)*N*8 bytes)
-            h->x2_ring = 5;
             if (const char *env = getenv("WRP_RING")) h->x2_ring = atoi(env);
-            if (h->x2_ring < 3) h->x2_ring = 3;
+            if (const char *env = getenv("WRP_LAG")) h->x2_lag = atoi(env);
+            if (h->x2_lag < 1) h->x2_lag = 1;
+            if (h->x2_ring < h->x2_lag + 2) h->x2_ring = h->x2_lag + 2; // a tile may only wait for earlier queue items
             if (h->x2_ring > 64) h->x2_ring = 64;
             h->smax = 1024;
             h->chunk = h->smax;
@@ -383,7 +384,7 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
             }
             if (h->persistent) {
                 ProfScope ps(h, st, 4);
-                CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->ctrl, h->smax, h->fused, M, N,
+                CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->x2_lag, h->ctrl, h->smax, h->fused, M, N,
                                              C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, st));
                 h->launches++;
             } else {

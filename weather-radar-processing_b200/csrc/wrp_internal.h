@@ -81,7 +81,8 @@ struct wrp_handle {
     int chunk = 1;
     // persistent form: x2 is a ring of `ring` sector slots; ctrl holds the work/dependency counters
     bool persistent = false;
-    int x2_ring = 5;
+    int x2_ring = 7; // sector slots of the x2 hand-off ring
+    int x2_lag = 3;  // Doppler blocks of sector t are queued after the range tiles of sector t + lag
     int *ctrl = nullptr;
     int smax = 1024; // sectors per persistent launch
 
@@ -119,7 +120,8 @@ cudaError_t launch_doppler(const float2 *x2, float *out, float *power, const Fus
 bool persistent_supported(int M, int N);
 cudaError_t persistent_setup();
 int persistent_ctrl_ints(int smax);
-cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int *ctrl,
+cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
+                              int *ctrl,
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
                               float calib, float taps_sum, int sm_count, cudaStream_t st);
 

@@ -63,9 +63,19 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 16-byte async copy global -> shared; the input is streamed once, so it is marked evict-first
+// in L2 and does not push the x2 ring out
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint64_t pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
+                 "l"(pol)
+                 : "memory");
 }
 // arrive on `bar` once every cp.async this thread has issued so far has landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
@@ -83,6 +93,15 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void red_release_add(int *p)
 {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+// probe without the L1 invalidate an acquire load carries (thread 0's warp would sit on it): the
+// counter is bumped by a release (data is in L2 before the count moves) and everything read
+// under it is fetched by bulk async copies straight from L2, issued after the value is seen
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void spin_until(const int *p, int target)
 {
@@ -187,7 +206,7 @@ __device__ __forceinline__ bool dep_ready(const Item &it, const PersistParams &p
 {
     int target;
     const int *dep = item_dep(it, p, target);
-    return dep == nullptr || ld_acquire(dep) >= target;
+    return dep == nullptr || ld_relaxed(dep) >= target;
 }
 __device__ __forceinline__ void dep_wait(const Item &it, const PersistParams &p)
 {
@@ -229,8 +248,9 @@ __device__ __forceinline__ void issue_load_a(const Item &it, const PersistParams
     const uint8_t *src = (const uint8_t *)p.iq + ((size_t)(it.sector * p.C + ch) * 1024 + (tid >> 2)) * (N * 8) +
                          tile * 64 + (tid & 3) * 16;
     uint8_t *dst = buf + tid * 16;
+    const uint64_t pol = policy_evict_first();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 4096, src + (size_t)k * 64 * (N * 8));
+    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 4096, src + (size_t)k * 64 * (N * 8), pol);
     cp_async_arrive(bar);
 }
 
@@ -293,6 +313,9 @@ __global__ void __launch_bounds__(256, 2)
         ++it_count;
         int nxt;
         bool ready; // next item's dependency was met when probed (CTA-uniform)
+        // claim the next queue slot now; the atomic's round trip hides behind this item's first pass
+        int claimed = 0, claimed_ready = 1;
+        if (tid == 0) claimed = atomicAdd(p.ctrl, 1);
         if (it.kind == 0) {
             mbar_wait(&mbar_a, phase_a);
             phase_a ^= 1;
@@ -330,6 +353,10 @@ __global__ void __launch_bounds__(256, 2)
                 });
             }
             fft_dit<R, -1>(v);
+            if (tid == 0) {
+                claimed = claimed < p.total_items ? claimed : -1;
+                if (claimed >= 0) claimed_ready = (int)dep_ready(decode_item(claimed, p), p);
+            }
             __syncwarp();
             {
                 // Z[ka][b] goes to row 32 ka + (b ^ (ka & 1)): same 4-row x 64 B footprint per warp
@@ -360,9 +387,8 @@ __global__ void __launch_bounds__(256, 2)
                 });
             }
             if (tid == 0) {
-                const int n = atomicAdd(p.ctrl, 1);
-                s_next[nslot] = n < p.total_items ? n : -1;
-                s_ready[nslot] = n < p.total_items ? (int)dep_ready(decode_item(n, p), p) : 1;
+                s_next[nslot] = claimed;
+                s_ready[nslot] = claimed_ready;
             }
             __syncthreads(); // every shared-memory read of this item is done; s_next is visible
             nxt = s_next[nslot];
@@ -427,6 +453,10 @@ __global__ void __launch_bounds__(256, 2)
                     });
                 }
             }
+            if (tid == 0) {
+                claimed = claimed < p.total_items ? claimed : -1;
+                if (claimed >= 0) claimed_ready = (int)dep_ready(decode_item(claimed, p), p);
+            }
             __syncwarp();
             float2 u[32];
             const int rsel = RPW == 2 ? (lane >> 4) : 0;
@@ -443,9 +473,8 @@ __global__ void __launch_bounds__(256, 2)
                 });
             }
             if (tid == 0) {
-                const int n = atomicAdd(p.ctrl, 1);
-                s_next[nslot] = n < p.total_items ? n : -1;
-                s_ready[nslot] = n < p.total_items ? (int)dep_ready(decode_item(n, p), p) : 1;
+                s_next[nslot] = claimed;
+                s_ready[nslot] = claimed_ready;
             }
             __syncthreads();
             if (tid == 0 && pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
@@ -552,7 +581,8 @@ cudaError_t persistent_setup()
 }
 
 // One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
-cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int *ctrl,
+cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
+                              int *ctrl,
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
                               float calib, float taps_sum, int sm_count, cudaStream_t st)
 {
@@ -573,7 +603,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.N = N;
     p.half_m = M / 2;
     p.ring = ring;
-    p.lag = ring >= 5 ? 2 : 1;
+    p.lag = lag;
     const int rows_b = TILE_BYTES / (N * 8);
     p.tiles_a = (N / 8) * C;
     p.pair_blocks = C >= 2 ? (M / 2) / (rows_b / 2) : 0;
