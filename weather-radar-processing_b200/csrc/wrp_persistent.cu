@@ -18,6 +18,8 @@
 // Cross-CTA ordering: per-sector completion counters (release: __threadfence + atomicAdd,
 // acquire: ld.acquire.gpu spin by the one thread that issues the dependent bulk copy).  An item
 // only ever waits for items earlier in the queue, which are held by running CTAs: no deadlock.
+#include <cstdlib>
+
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
 
@@ -63,19 +65,13 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ uint64_t policy_evict_first()
+// 16-byte async copy global -> shared (L1 bypass).  An L2 evict-first cache hint was tried here
+// (cp.async ... .L2::cache_hint): ptxas 12.9 allocated an odd uniform register for the LDGSTS
+// descriptor at one call site and the warp trapped with "illegal instruction", so the L2 priority
+// is left at the default (st/ld eviction-priority qualifiers need 256-bit vectors on sm_100).
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// 16-byte async copy global -> shared; the input is streamed once, so it is marked evict-first
-// in L2 and does not push the x2 ring out
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint64_t pol)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
-                 "l"(pol)
-                 : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 // arrive on `bar` once every cp.async this thread has issued so far has landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
@@ -122,13 +118,14 @@ struct PersistParams {
     int S, C, N, half_m;
     int ring, lag;
     int tiles_a, blocks_b, pair_blocks;
+    int tile_bytes;
+    int debug; // WRP_DEBUG bisect switches (development only)
     int n1, n2, n3, b3_first; // queue regions (see decode_item)
     int total_items;
     int smax;
     float range_res, calib, taps_sum;
 };
 constexpr int CTRL_A = 32;
-constexpr int TILE_BYTES = 65536;
 // shared-memory copies of the small tables (no L1 dependence: the acquire loads of the
 // dependency counters invalidate L1)
 // rows are padded by 16 B so that the 128-bit reads of lanes holding different rows hit
@@ -137,7 +134,9 @@ constexpr int WRC_ROW = 32 * 4 + 16;   // wr(i)*c transposed [32][32] float
 constexpr int TWA_ROW = 32 * 8 + 16;   // range inter-pass twiddles [32][32] float2
 constexpr int TAB_WRC = 32 * WRC_ROW;
 constexpr int TAB_TWA = 32 * TWA_ROW;
-template <int R1B> struct Tables {
+// T = columns per range tile = warps per CTA; the tile buffer holds T*8 KiB
+template <int R1B, int T> struct Tables {
+    static constexpr int TILE_BYTES = T * 8192;
     static constexpr int N = 32 * R1B;
     static constexpr int TWB_ROW = R1B * 8 + 16; // Doppler inter-pass twiddles [32][R1B] float2
     static constexpr int WD = N * 4;             // Doppler window
@@ -218,11 +217,12 @@ __device__ __forceinline__ void dep_wait(const Item &it, const PersistParams &p)
 // Doppler block (thread 0): two 32 KiB (or one 64 KiB) contiguous bulk copies from the x2 ring
 __device__ __forceinline__ void issue_load_b(const Item &it, const PersistParams &p, uint8_t *buf, uint64_t *bar)
 {
+    const int TILE_BYTES = p.tile_bytes;
     fence_proxy_async();
     mbar_expect_tx(bar, TILE_BYTES);
     const int slot = it.sector % p.ring;
     const size_t row_bytes = (size_t)p.N * sizeof(float2);
-    const int rows = TILE_BYTES / (int)row_bytes; // 16 (N=512) or 8 (N=1024)
+    const int rows = TILE_BYTES / (int)row_bytes;
     if (it.sub < p.pair_blocks) {
         const int g0 = it.sub * (rows / 2);
         const uint8_t *hh = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
@@ -237,33 +237,38 @@ __device__ __forceinline__ void issue_load_b(const Item &it, const PersistParams
     }
 }
 
-// Range tile (all 256 threads): 1024 rows x 64 B, 16 B per cp.async (a warp covers 8 rows x 64 B).
+// Range tile (all threads): 1024 rows x T*8 B, 16 B per cp.async (a warp covers 512 contiguous-row bytes).
 // A 4-D TMA box was tried first: one 64 B row per request throttles the TMA unit (~5 us per tile).
-template <int N>
+template <int N, int T>
 __device__ __forceinline__ void issue_load_a(const Item &it, const PersistParams &p, uint8_t *buf, uint64_t *bar,
                                              int tid)
 {
-    constexpr int tiles_per_plane = N / 8;
+    constexpr int tiles_per_plane = N / T;
+    constexpr int CPR = T / 2; // 16-byte chunks per tile row
     const int ch = it.sub / tiles_per_plane, tile = it.sub - ch * tiles_per_plane;
-    const uint8_t *src = (const uint8_t *)p.iq + ((size_t)(it.sector * p.C + ch) * 1024 + (tid >> 2)) * (N * 8) +
-                         tile * 64 + (tid & 3) * 16;
+    const uint8_t *src = (const uint8_t *)p.iq + ((size_t)(it.sector * p.C + ch) * 1024 + (tid / CPR)) * (N * 8) +
+                         tile * (T * 8) + (tid % CPR) * 16;
     uint8_t *dst = buf + tid * 16;
-    const uint64_t pol = policy_evict_first();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 4096, src + (size_t)k * 64 * (N * 8), pol);
+    for (int k = 0; k < 16; ++k) cp_async16(dst + k * (64 * T * 8), src + (size_t)k * 64 * (N * 8));
     cp_async_arrive(bar);
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <int R1B> // Doppler length N = 32 * R1B
-__global__ void __launch_bounds__(256, 2)
+template <int R1B, int T> // Doppler length N = 32 * R1B; T columns per range tile = warps per CTA
+__global__ void __launch_bounds__(32 * T, 16 / T)
     chain_persistent_kernel(const PersistParams p)
 {
     constexpr int R = 32; // range FFT 32 x 32 (M = 1024)
     constexpr int N = 32 * R1B;
+    constexpr int THREADS = 32 * T;
+    using Tab = Tables<R1B, T>;
+    constexpr int TILE_BYTES = Tab::TILE_BYTES;
+    constexpr int PITCH = T * 8;                   // bytes per tile row
+    constexpr int SW = 128 / PITCH - 1;            // row-swizzle mask of the in-place exchange
     constexpr int ROWS_B = TILE_BYTES / (N * 8);   // Doppler rows per block
-    constexpr int RPW = ROWS_B / 8;                // rows per warp
-    using Tab = Tables<R1B>;
+    constexpr int RPW = ROWS_B / T;                // rows per warp
+    static_assert(RPW == 1 || RPW == 2, "Doppler rows per warp");
     extern __shared__ __align__(1024) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar_a, mbar_b; // range tiles (256 cp.async arrivals) / Doppler blocks (tx bytes)
     __shared__ int s_next[2], s_ready[2];
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(256, 2)
         // copy the tables into (row-padded) shared memory, 16 B per step
         auto copy_rows = [&](int off, const void *src, int rows, int row_bytes, int row_pitch) {
             const int per_row = row_bytes / 16;
-            for (int i = tid; i < rows * per_row; i += 256) {
+            for (int i = tid; i < rows * per_row; i += THREADS) {
                 const int r = i / per_row, q = i - r * per_row;
                 *reinterpret_cast<float4 *>(tile + off + r * row_pitch + q * 16) =
                     __ldg(reinterpret_cast<const float4 *>(src) + i);
@@ -285,27 +290,36 @@ __global__ void __launch_bounds__(256, 2)
         copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
         copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
     }
+    if (p.debug & 1) return;
     int pending = -1; // sector whose range tile this CTA finished but has not signalled yet
     if (tid == 0) {
-        mbar_init(&mbar_a, 256);
+        mbar_init(&mbar_a, THREADS);
         mbar_init(&mbar_b, 1);
         const int first = atomicAdd(p.ctrl, 1);
         s_next[0] = first < p.total_items ? first : -1;
     }
     __syncthreads();
     int cur = s_next[0];
+    if ((p.debug & 2) && cur >= 0 && decode_item(cur, p).kind == 1) return;
+    if ((p.debug & 4) && cur >= 0) return;
     if (cur >= 0) {
         const Item first = decode_item(cur, p);
         if (tid == 0) dep_wait(first, p);
         if (first.kind == 0) {
             __syncthreads();
-            issue_load_a<N>(first, p, tile, &mbar_a, tid);
+            issue_load_a<N, T>(first, p, tile, &mbar_a, tid);
         } else if (tid == 0) {
             issue_load_b(first, p, tile, &mbar_b);
         }
     }
     uint32_t phase_a = 0, phase_b = 0;
     int it_count = 0;
+    if (p.debug & 2) {
+        if (cur >= 0) {
+            if (decode_item(cur, p).kind == 0) mbar_wait(&mbar_a, 0); else mbar_wait(&mbar_b, 0);
+        }
+        return;
+    }
 
     while (cur >= 0) {
         const Item it = decode_item(cur, p);
@@ -326,15 +340,15 @@ __global__ void __launch_bounds__(256, 2)
 
         if (it.kind == 0) {
             // ================= range tile =================
-            const int c = tid & 7, b = tid >> 3;
-            constexpr int tiles_per_plane = N / 8;
-            const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * 8 + c;
+            const int c = tid % T, b = tid / T;
+            constexpr int tiles_per_plane = N / T;
+            const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * T + c;
             float2 v[R];
             {
-                const uint8_t *src = tile + b * 64 + c * 8;
+                const uint8_t *src = tile + b * PITCH + c * 8;
                 static_for<R>([&](auto ai) {
                     constexpr int a = decltype(ai)::value;
-                    v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * 64));
+                    v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
                 });
                 const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
                 const float4 *w4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_WRC + b * WRC_ROW);
@@ -359,18 +373,20 @@ __global__ void __launch_bounds__(256, 2)
             }
             __syncwarp();
             {
-                // Z[ka][b] goes to row 32 ka + (b ^ (ka & 1)): same 4-row x 64 B footprint per warp
-                // (in place), and pass 2's two ka per half-warp fall into different 64 B halves
+                // Z[ka][b] goes to row 32 ka + (b ^ (ka & SW)): the warp keeps its own row footprint
+                // (in place), and the 128/PITCH values of ka met by one shared-memory wavefront of
+                // pass 2 fall into different PITCH-byte slices of a 128-byte bank line
                 const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWA + b * TWA_ROW);
-                uint8_t *d_even = tile + b * 64 + c * 8;
-                uint8_t *d_odd = tile + (b ^ 1) * 64 + c * 8;
+                uint8_t *d_sw[SW + 1];
+#pragma unroll
+                for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = tile + (b ^ sx) * PITCH + c * 8;
                 static_for<R / 2>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
                     const float4 w = t4[q];
                     const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
                     const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
-                    *reinterpret_cast<float2 *>(d_even + (2 * q) * (R * 64)) = y0;
-                    *reinterpret_cast<float2 *>(d_odd + (2 * q + 1) * (R * 64)) = y1;
+                    *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
+                    *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
                 });
             }
             __syncthreads();
@@ -378,12 +394,11 @@ __global__ void __launch_bounds__(256, 2)
             pending = -1;
             const int ka = b;
             {
-                const int par = (ka & 1) * 64;
-                const uint8_t *s_even = tile + ka * (R * 64) + c * 8 + par; // even b: row b + (ka&1)
-                const uint8_t *s_odd = tile + ka * (R * 64) + c * 8 - par;  // odd b:  row b - (ka&1)
+                // row 32 ka + (bb ^ (ka & SW)): the swizzle bits do not overlap the rest of the address
+                const uint32_t off_sw = (uint32_t)(ka * (R * PITCH) + c * 8) | (uint32_t)((ka & SW) * PITCH);
                 static_for<R>([&](auto bi) {
                     constexpr int bb = decltype(bi)::value;
-                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(((bb & 1) ? s_odd : s_even) + bb * 64);
+                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(tile + (off_sw ^ (uint32_t)(bb * PITCH)));
                 });
             }
             if (tid == 0) {
@@ -396,7 +411,7 @@ __global__ void __launch_bounds__(256, 2)
             if (nxt >= 0 && ready) {
                 const Item nit = decode_item(nxt, p);
                 if (nit.kind == 0)
-                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                    issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
                     issue_load_b(nit, p, tile, &mbar_b);
             }
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(256, 2)
             if (nxt >= 0 && ready) {
                 const Item nit = decode_item(nxt, p);
                 if (nit.kind == 0)
-                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                    issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
                     issue_load_b(nit, p, tile, &mbar_b);
             }
@@ -525,7 +540,7 @@ __global__ void __launch_bounds__(256, 2)
             } else {
                 if (ka == 0) p_row[my_row] = pw;
                 __syncthreads();
-                if (pair && tid < ROWS_B / 2) {
+                if (pair && tid < ROWS_B / 2) { // N = 1024: (hh, vv) rows sit in different warps
                     const int g = g0 + tid;
                     const float p_hh = p_row[tid], p_vv = p_row[ROWS_B / 2 + tid];
                     const float rg = (float)g * p.range_res;
@@ -557,7 +572,7 @@ __global__ void __launch_bounds__(256, 2)
                 if (tid == 0) dep_wait(nit, p);
                 if (nit.kind == 0) {
                     __syncthreads();
-                    issue_load_a<N>(nit, p, tile, &mbar_a, tid);
+                    issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
                 } else if (tid == 0) {
                     issue_load_b(nit, p, tile, &mbar_b);
                 }
@@ -571,13 +586,29 @@ __global__ void __launch_bounds__(256, 2)
 bool persistent_supported(int M, int N) { return M == 1024 && (N == 512 || N == 1024); }
 int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
 
+static int tile_cols()
+{
+    static int t = 0;
+    if (!t) {
+        const char *env = getenv("WRP_TILE_COLS");
+        t = env && atoi(env) == 4 ? 4 : 8; // 8 columns (64-byte row segments) measured 24 % faster than 4
+    }
+    return t;
+}
+
 cudaError_t persistent_setup()
 {
-    cudaError_t e = cudaFuncSetAttribute(chain_persistent_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Tables<16>::SMEM);
+    cudaError_t e;
+#define WRP_SET(R1B, T)                                                                                      \
+    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                             Tables<R1B, T>::SMEM);                                                          \
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(chain_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Tables<32>::SMEM);
+    WRP_SET(16, 8)
+    WRP_SET(16, 4)
+    WRP_SET(32, 8)
+    WRP_SET(32, 4)
+#undef WRP_SET
+    return cudaSuccess;
 }
 
 // One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
@@ -604,8 +635,10 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.half_m = M / 2;
     p.ring = ring;
     p.lag = lag;
-    const int rows_b = TILE_BYTES / (N * 8);
-    p.tiles_a = (N / 8) * C;
+    const int T = tile_cols();
+    p.tile_bytes = T * 8192;
+    const int rows_b = p.tile_bytes / (N * 8);
+    p.tiles_a = (N / T) * C;
     p.pair_blocks = C >= 2 ? (M / 2) / (rows_b / 2) : 0;
     p.blocks_b = p.pair_blocks + ((C & 1) ? (M / 2) / rows_b : 0);
     const int L = p.lag, S = n_sectors;
@@ -615,18 +648,23 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.b3_first = S > L ? S - L : 0;
     p.total_items = S * (p.tiles_a + p.blocks_b);
     p.smax = smax;
+    p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
     p.calib = calib;
     p.taps_sum = taps_sum;
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
     if (e != cudaSuccess) return e;
-    int grid = 2 * sm_count;
+    int grid = (16 / T) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
-    if (N == 512)
-        chain_persistent_kernel<16><<<grid, 256, Tables<16>::SMEM, st>>>(p);
+    if (N == 512 && T == 8)
+        chain_persistent_kernel<16, 8><<<grid, 256, Tables<16, 8>::SMEM, st>>>(p);
+    else if (N == 512)
+        chain_persistent_kernel<16, 4><<<grid, 128, Tables<16, 4>::SMEM, st>>>(p);
+    else if (T == 8)
+        chain_persistent_kernel<32, 8><<<grid, 256, Tables<32, 8>::SMEM, st>>>(p);
     else
-        chain_persistent_kernel<32><<<grid, 256, Tables<32>::SMEM, st>>>(p);
+        chain_persistent_kernel<32, 4><<<grid, 128, Tables<32, 4>::SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
