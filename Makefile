@@ -11,7 +11,22 @@ NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC
 LIB      := $(PKG)/libwrp.so
 OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
 
-all: $(LIB) oracle
+HOSTLIB  := $(PKG)/libwrphost.so
+HOSTSRC  := $(HOST)/dimension.cpp $(HOST)/sector.cpp $(HOST)/floats.c $(HOST)/radar_processor.cpp $(HOST)/stage_dump.cpp
+HOSTBINS := $(HOST)/wrp_chain $(HOST)/host_selftest
+
+all: $(LIB) $(HOSTLIB) $(HOSTBINS) oracle
+
+# C++ host mirror of the reference's API, on top of the C ABI only
+$(HOSTLIB): $(HOSTSRC) $(HOST)/*.h include/wrp.h $(LIB)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -o $@ $(HOST)/dimension.cpp $(HOST)/sector.cpp -x c++ $(HOST)/floats.c -x none \
+	    $(HOST)/radar_processor.cpp $(HOST)/stage_dump.cpp -L$(PKG) -lwrp -Wl,-rpath,'$$ORIGIN'
+
+$(HOST)/wrp_chain: $(HOST)/wrp_chain.cpp $(HOSTLIB)
+	$(CXX) -O2 -std=c++17 -o $@ $< -L$(PKG) -lwrphost -lwrp -Wl,-rpath,'$$ORIGIN/..'
+
+$(HOST)/host_selftest: $(HOST)/host_selftest.cpp $(HOSTLIB)
+	$(CXX) -O2 -std=c++17 -o $@ $< -L$(PKG) -lwrphost -lwrp -Wl,-rpath,'$$ORIGIN/..'
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/wrp_internal.h $(CSRC)/wrp_fft.cuh include/wrp.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -26,6 +41,6 @@ oracle:
 	$(MAKE) -C oracle liboracle.so
 
 clean:
-	rm -f $(OBJS) $(LIB)
+	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(HOSTBINS)
 
 .PHONY: all oracle clean

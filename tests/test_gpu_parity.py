@@ -295,3 +295,39 @@ def test_extreme_inputs_match_oracle(wrp, oracle):
     assert np.all(np.isneginf(out[1][1:, 0])) and np.all(np.isnan(out[1][:, 1]))
     # gate 0: (30*0)^2 * calib * 0 = 0 in both -> -inf
     assert np.isneginf(out[1][0, 0]) and np.isneginf(refz.zdb[0])
+
+
+def test_cpp_radar_processor_cli(wrp, oracle, sectors, refs, tmp_path):
+    """The C++ host mirror end to end: RadarProcessor(143, 1024, 512, 9, streams).start() fed from a
+    wire file through wrp_chain, ZdB written in the layout error.cpp reads, stage dumps in the
+    reference's text format; compared with the oracle and with the reference's own error metric."""
+    import os
+    import subprocess
+    exe = os.path.join(wrp.REPO_ROOT, "weather-radar-processing_b200", "host", "wrp_chain")
+    assert os.path.exists(exe), "run make / __graft_entry__.build()"
+    wire = np.concatenate([wrp.synth.to_wire(x) for x in sectors])
+    inp = tmp_path / "wire.bin"
+    wire.tofile(inp)
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([exe, "--in", str(inp), "--zdb-bin", str(tmp_path / "gpu.bin"), "--result-dir", str(dump),
+                        "--dump-dir", str(dump), "--batch", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "processed 3 sectors" in r.stdout
+    zdb = np.fromfile(tmp_path / "gpu.bin", np.float32).reshape(3, M // 2)
+    for s in range(3):
+        assert np.isneginf(zdb[s, 0]) and np.max(np.abs(zdb[s, 1:] - refs[s].zdb[1:])) <= DB_TOL
+        res = np.genfromtxt(dump / f"99result.{s}.gpu.out")
+        assert np.max(np.abs(res[1:, 0] - refs[s].zdb[1:])) <= DB_TOL and np.max(np.abs(res[:, 1] - refs[s].zdr)) <= DB_TOL
+    # error.cpp's metric through the CLI: relative L2 of ZdB against the oracle's float32 ZdB
+    refs[0].zdb.astype(np.float32).tofile(tmp_path / "cpu.bin")
+    e = subprocess.run([exe, "--error", str(tmp_path / "cpu.bin"), str(tmp_path / "gpu.bin"), "512"],
+                       capture_output=True, text=True)
+    assert float(e.stdout) < 1e-5
+    # stage dumps of sector 0 (hh) parse with the reference-format reader and match the oracle at
+    # the 6 printed digits
+    for st, name in (("02fft1", "s02_fft1"), ("04abs", "s04_abs"), ("08pow", "s08_pow")):
+        got = wrp.dumpio.read_dump(str(dump / f"{st}.gpu.out"))
+        want = refs[0].stages[name][0]
+        den = np.abs(want).max(axis=0 if st == "02fft1" else -1, keepdims=True)
+        assert np.max(np.abs(got - want) / den) <= 1e-4, st

@@ -141,3 +141,16 @@ def test_synthetic_formats_agree(wrp):
     assert len(text) == 2 * 2 * 16 * 8 and int(text[0]) == iq16[0, 0, 0, 0]
     b = wrp.synth.make_batch(16, 8, 5, fmt="planar", distinct=2)
     assert b.shape == (5, 3, 16, 8) and np.array_equal(b[0], b[2]) and not np.array_equal(b[0], b[1])
+
+
+def test_cpp_host_mirror_selftest(wrp):
+    """The C++ mirror of the reference's host API (Dimension3/4, Sector, floats codec, packets,
+    RadarProcessor's public dims, dump writers) — CPU-only executable built by `make`."""
+    import subprocess
+    exe = os.path.join(wrp.REPO_ROOT, "weather-radar-processing_b200", "host", "host_selftest")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", wrp.REPO_ROOT, os.path.relpath(exe, wrp.REPO_ROOT)], check=True,
+                       capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host selftest: ok" in r.stdout
