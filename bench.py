@@ -122,7 +122,7 @@ def cpu_baseline_port(sample_sectors: int):
     wire = synth.make_batch(M, N, sample_sectors, fmt="wire", distinct=2)
     oracle.batch_wire_f32(wire[:1], 1, M, N, C, 1)  # warm the page cache / libm
     t0 = time.perf_counter()
-    _, used = oracle.batch_wire_f32(wire, sample_sectors, M, N, C, 0)
+    _, used = oracle.batch_wire_f32(wire, sample_sectors, M, N, C, cores)
     dt = time.perf_counter() - t0
     return {"value": sample_sectors / dt, "unit": "sectors/s", "cores": used, "kind": "port",
             "sample": f"{sample_sectors} synthetic wire-format sectors 1024x512x3, oracle float chain "
@@ -163,7 +163,7 @@ def run_reference(args):
         wire = synth.make_batch(M, N, n, fmt="wire", distinct=2)
 
         def one_step():
-            oracle.batch_wire_f32(wire, n, M, N, C, 0)
+            oracle.batch_wire_f32(wire, n, M, N, C, cores)
             return n
         desc = f"oracle float chain (port of read_single.cc), OpenMP {cores} threads, {n} sectors per step"
     for _ in range(warmup):
@@ -300,7 +300,10 @@ def run_ours(args):
         except Exception:
             pass
         chain_gbs = value / world * ALGO_BYTES_C64 / 1e9
-        cpu = cpu_baseline_port(args.cpu_sample if args.cpu_sample > 0 else max(2 * (os.cpu_count() or 1), 16))
+        # reported on rank 0 at N = 1 only (torchrun also pins OMP_NUM_THREADS=1 on its workers)
+        cpu = None
+        if world == 1:
+            cpu = cpu_baseline_port(args.cpu_sample if args.cpu_sample > 0 else max(2 * (os.cpu_count() or 1), 16))
         line = {
             "metric": "sectors_per_s", "value": value, "unit": "sectors/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,

@@ -137,6 +137,17 @@ template <int R, int SIGN> __device__ __forceinline__ void fft_dit(float2 (&v)[R
     if constexpr (R >= 32) dit_stage<R, 16, SIGN>(v);
 }
 
+// Same network without its first stage (span 1): the caller has already formed
+// (v[2m], v[2m+1]) <- (v[2m] + v[2m+1], v[2m] - v[2m+1]), e.g. fused with a window multiply.
+template <int R, int SIGN> __device__ __forceinline__ void fft_dit_after_stage1(float2 (&v)[R])
+{
+    static_assert(R == 4 || R == 8 || R == 16 || R == 32, "radix");
+    dit_stage<R, 2, SIGN>(v);
+    if constexpr (R >= 8) dit_stage<R, 4, SIGN>(v);
+    if constexpr (R >= 16) dit_stage<R, 8, SIGN>(v);
+    if constexpr (R >= 32) dit_stage<R, 16, SIGN>(v);
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
     return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));

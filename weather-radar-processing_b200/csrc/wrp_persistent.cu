@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
     static_assert(RPW == 1 || RPW == 2, "Doppler rows per warp");
     extern __shared__ __align__(1024) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar_a, mbar_b; // range tiles (256 cp.async arrivals) / Doppler blocks (tx bytes)
-    __shared__ int s_next[2], s_ready[2];
+    __shared__ int4 s_item[2]; // next item decoded by thread 0: (kind, sector, sub, ready); kind < 0: queue empty
     __shared__ float p_row[ROWS_B];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,39 +296,34 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         mbar_init(&mbar_a, THREADS);
         mbar_init(&mbar_b, 1);
         const int first = atomicAdd(p.ctrl, 1);
-        s_next[0] = first < p.total_items ? first : -1;
+        Item f{-1, 0, 0};
+        if (first < p.total_items) f = decode_item(first, p);
+        s_item[0] = make_int4(f.kind, f.sector, f.sub, 1);
     }
     __syncthreads();
-    int cur = s_next[0];
-    if ((p.debug & 2) && cur >= 0 && decode_item(cur, p).kind == 1) return;
-    if ((p.debug & 4) && cur >= 0) return;
-    if (cur >= 0) {
-        const Item first = decode_item(cur, p);
-        if (tid == 0) dep_wait(first, p);
-        if (first.kind == 0) {
+    Item it{s_item[0].x, s_item[0].y, s_item[0].z};
+    if (p.debug & 4) return;
+    if (it.kind >= 0) {
+        if (tid == 0) dep_wait(it, p);
+        if (it.kind == 0) {
             __syncthreads();
-            issue_load_a<N, T>(first, p, tile, &mbar_a, tid);
+            issue_load_a<N, T>(it, p, tile, &mbar_a, tid);
         } else if (tid == 0) {
-            issue_load_b(first, p, tile, &mbar_b);
+            issue_load_b(it, p, tile, &mbar_b);
         }
     }
     uint32_t phase_a = 0, phase_b = 0;
     int it_count = 0;
-    if (p.debug & 2) {
-        if (cur >= 0) {
-            if (decode_item(cur, p).kind == 0) mbar_wait(&mbar_a, 0); else mbar_wait(&mbar_b, 0);
-        }
-        return;
-    }
 
-    while (cur >= 0) {
-        const Item it = decode_item(cur, p);
+    while (it.kind >= 0) {
         const int nslot = (it_count + 1) & 1;
         ++it_count;
-        int nxt;
-        bool ready; // next item's dependency was met when probed (CTA-uniform)
-        // claim the next queue slot now; the atomic's round trip hides behind this item's first pass
-        int claimed = 0, claimed_ready = 1;
+        Item nit;   // next item (CTA-uniform after the buffer-release barrier)
+        bool ready; // its dependency was met when probed
+        // thread 0 claims the next queue slot now — the atomic's round trip hides behind this item's
+        // first pass — and decodes it for everybody
+        int claimed = 0;
+        int4 nx = make_int4(-1, 0, 0, 1);
         if (tid == 0) claimed = atomicAdd(p.ctrl, 1);
         if (it.kind == 0) {
             mbar_wait(&mbar_a, phase_a);
@@ -350,26 +345,30 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     constexpr int a = decltype(ai)::value;
                     v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
                 });
+                // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage:
+                // the span-1 partners of the bit-reversed network are rows a and a + 16
                 const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
                 const float4 *w4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_WRC + b * WRC_ROW);
-                static_for<R / 4>([&](auto qi) {
+                static_for<R / 8>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = w4[q];
-                    const float w0 = w.x * wdj, w1 = w.y * wdj, w2 = w.z * wdj, w3 = w.w * wdj;
-                    v[brev<R>(4 * q + 0)].x *= w0;
-                    v[brev<R>(4 * q + 0)].y *= w0;
-                    v[brev<R>(4 * q + 1)].x *= w1;
-                    v[brev<R>(4 * q + 1)].y *= w1;
-                    v[brev<R>(4 * q + 2)].x *= w2;
-                    v[brev<R>(4 * q + 2)].y *= w2;
-                    v[brev<R>(4 * q + 3)].x *= w3;
-                    v[brev<R>(4 * q + 3)].y *= w3;
+                    const float4 wlo = w4[q], whi = w4[q + R / 8];
+                    const float wl[4] = {wlo.x * wdj, wlo.y * wdj, wlo.z * wdj, wlo.w * wdj};
+                    const float wh[4] = {whi.x * wdj, whi.y * wdj, whi.z * wdj, whi.w * wdj};
+                    static_for<4>([&](auto ei) {
+                        constexpr int e = decltype(ei)::value;
+                        constexpr int sa = brev<R>(4 * q + e); // even slot; its partner row a + R/2 sits in sa + 1
+                        static_assert(brev<R>(4 * q + e + R / 2) == sa + 1, "span-1 partner");
+                        const float2 A = v[sa], B = v[sa + 1];
+                        const float tx = B.x * wh[e], ty = B.y * wh[e];
+                        v[sa] = make_float2(fmaf(A.x, wl[e], tx), fmaf(A.y, wl[e], ty));
+                        v[sa + 1] = make_float2(fmaf(A.x, wl[e], -tx), fmaf(A.y, wl[e], -ty));
+                    });
                 });
             }
-            fft_dit<R, -1>(v);
-            if (tid == 0) {
-                claimed = claimed < p.total_items ? claimed : -1;
-                if (claimed >= 0) claimed_ready = (int)dep_ready(decode_item(claimed, p), p);
+            fft_dit_after_stage1<R, -1>(v);
+            if (tid == 0 && claimed < p.total_items) {
+                const Item c = decode_item(claimed, p);
+                nx = make_int4(c.kind, c.sector, c.sub, (int)dep_ready(c, p));
             }
             __syncwarp();
             {
@@ -401,15 +400,11 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(tile + (off_sw ^ (uint32_t)(bb * PITCH)));
                 });
             }
-            if (tid == 0) {
-                s_next[nslot] = claimed;
-                s_ready[nslot] = claimed_ready;
-            }
+            if (tid == 0) s_item[nslot] = nx;
             __syncthreads(); // every shared-memory read of this item is done; s_next is visible
-            nxt = s_next[nslot];
-            ready = s_ready[nslot] != 0;
-            if (nxt >= 0 && ready) {
-                const Item nit = decode_item(nxt, p);
+            nit = Item{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z};
+            ready = s_item[nslot].w != 0;
+            if (nit.kind >= 0 && ready) {
                 if (nit.kind == 0)
                     issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
@@ -440,7 +435,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     tw[2 * q] = make_float2(w.x, w.y);
                     tw[2 * q + 1] = make_float2(w.z, w.w);
                 });
-#pragma unroll
+#pragma unroll 1
                 for (int rr = 0; rr < RPW; ++rr) {
                     uint8_t *row = tile + (size_t)(warp + rr * (ROWS_B / 2)) * (N * 8);
                     float2 v[R1B];
@@ -468,9 +463,9 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     });
                 }
             }
-            if (tid == 0) {
-                claimed = claimed < p.total_items ? claimed : -1;
-                if (claimed >= 0) claimed_ready = (int)dep_ready(decode_item(claimed, p), p);
+            if (tid == 0 && claimed < p.total_items) {
+                const Item c = decode_item(claimed, p);
+                nx = make_int4(c.kind, c.sector, c.sub, (int)dep_ready(c, p));
             }
             __syncwarp();
             float2 u[32];
@@ -487,17 +482,13 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
                 });
             }
-            if (tid == 0) {
-                s_next[nslot] = claimed;
-                s_ready[nslot] = claimed_ready;
-            }
+            if (tid == 0) s_item[nslot] = nx;
             __syncthreads();
             if (tid == 0 && pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
             pending = -1;
-            nxt = s_next[nslot];
-            ready = s_ready[nslot] != 0;
-            if (nxt >= 0 && ready) {
-                const Item nit = decode_item(nxt, p);
+            nit = Item{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z};
+            ready = s_item[nslot].w != 0;
+            if (nit.kind >= 0 && ready) {
                 if (nit.kind == 0)
                     issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
@@ -559,16 +550,15 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         }
         // the probe found the next item's dependency unmet: this CTA's own item is signalled
         // (or about to be, by its other warps), so a blocking wait is safe now
-        if (nxt < 0 || !ready) {
+        if (nit.kind < 0 || !ready) {
             // leaving the loop, or about to block on a dependency: publish the pending tile first
-            // (the item waited for may be this CTA's own).  nxt and ready are CTA-uniform.
+            // (the item waited for may be this CTA's own).  nit and ready are CTA-uniform.
             if (pending >= 0) {
                 __syncthreads();
                 if (tid == 0) red_release_add(p.ctrl + CTRL_A + pending);
                 pending = -1;
             }
-            if (nxt >= 0) {
-                const Item nit = decode_item(nxt, p);
+            if (nit.kind >= 0) {
                 if (tid == 0) dep_wait(nit, p);
                 if (nit.kind == 0) {
                     __syncthreads();
@@ -578,7 +568,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 }
             }
         }
-        cur = nxt;
+        it = nit;
     }
 }
 
