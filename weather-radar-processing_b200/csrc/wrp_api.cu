@@ -152,6 +152,17 @@ static int create_impl(wrp_handle *h)
             h->chunk = h->smax;
             CK(h, wrp::persistent_setup());
             CK(h, cudaMalloc((void **)&h->x2, inter * h->x2_ring));
+            if (const char *env = getenv("WRP_L2_PERSIST")) {
+                if (atoi(env) > 0) {
+                    // opt-in: carve persisting L2 out for the ring (a device-wide limit, hence not default)
+                    size_t want = inter * h->x2_ring;
+                    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+                    if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
+                    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                        h->l2_window = want;
+                    cudaGetLastError();
+                }
+            }
             CK(h, cudaMalloc((void **)&h->ctrl, sizeof(int) * wrp::persistent_ctrl_ints(h->smax)));
             CK(h, cudaMalloc((void **)&h->power, (size_t)c.max_batch * C * (M / 2) * sizeof(float)));
             if (c.input_fmt == WRP_FMT_WIRE_I16BE) {
@@ -385,7 +396,7 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
             if (h->persistent) {
                 ProfScope ps(h, st, 4);
                 CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->x2_lag, h->ctrl, h->smax, h->fused, M, N,
-                                             C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, st));
+                                             C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, h->l2_window, st));
                 h->launches++;
             } else {
                 {

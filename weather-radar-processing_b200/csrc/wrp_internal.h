@@ -85,6 +85,7 @@ struct wrp_handle {
     int x2_lag = 3;  // Doppler blocks of sector t are queued after the range tiles of sector t + lag
     int *ctrl = nullptr;
     int smax = 1024; // sectors per persistent launch
+    size_t l2_window = 0; // bytes of the x2 ring pinned in L2 per launch (0 = off)
 
     cudaStream_t compute_stream = nullptr; // all kernels of the host path run here (owns the scratch)
     std::vector<wrp::RingSlot> ring;
@@ -123,7 +124,7 @@ int persistent_ctrl_ints(int smax);
 cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
                               int *ctrl,
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
-                              float calib, float taps_sum, int sm_count, cudaStream_t st);
+                              float calib, float taps_sum, int sm_count, size_t l2_window_bytes, cudaStream_t st);
 
 // Staged path (wrp_staged.cu): the reference cascade, one stage per kernel.
 // Returns the number of kernels launched through *launches.

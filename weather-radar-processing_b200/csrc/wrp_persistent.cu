@@ -605,7 +605,7 @@ cudaError_t persistent_setup()
 cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
                               int *ctrl,
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
-                              float calib, float taps_sum, int sm_count, cudaStream_t st)
+                              float calib, float taps_sum, int sm_count, size_t l2_window_bytes, cudaStream_t st)
 {
     if (n_sectors == 0) return cudaSuccess;
     if (!persistent_supported(M, N) || n_sectors > smax) return cudaErrorInvalidValue;
@@ -647,15 +647,39 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     if (e != cudaSuccess) return e;
     int grid = (16 / T) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
-    if (N == 512 && T == 8)
-        chain_persistent_kernel<16, 8><<<grid, 256, Tables<16, 8>::SMEM, st>>>(p);
-    else if (N == 512)
-        chain_persistent_kernel<16, 4><<<grid, 128, Tables<16, 4>::SMEM, st>>>(p);
-    else if (T == 8)
-        chain_persistent_kernel<32, 8><<<grid, 256, Tables<32, 8>::SMEM, st>>>(p);
-    else
-        chain_persistent_kernel<32, 4><<<grid, 128, Tables<32, 4>::SMEM, st>>>(p);
-    return cudaGetLastError();
+
+    // Optional (WRP_L2_PERSIST=1, needs a persisting-L2 carve-out set by the caller of wrp_create):
+    // pin the x2 ring in L2 for this launch through an access-policy window, so the streamed
+    // input cannot push the hand-off rows out to DRAM.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * T);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int n_attr = 0;
+    if (l2_window_bytes > 0) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = (void *)x2_ring;
+        attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n_attr = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    if (N == 512 && T == 8) {
+        cfg.dynamicSmemBytes = Tables<16, 8>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 8>, p);
+    } else if (N == 512) {
+        cfg.dynamicSmemBytes = Tables<16, 4>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 4>, p);
+    } else if (T == 8) {
+        cfg.dynamicSmemBytes = Tables<32, 8>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 8>, p);
+    }
+    cfg.dynamicSmemBytes = Tables<32, 4>::SMEM;
+    return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 4>, p);
 }
 
 } // namespace wrp
