@@ -49,7 +49,8 @@ sys.path.insert(0, ROOT)
 M, N, C = 1024, 512, 3
 ALGO_BYTES_C64 = C * M * N * 8 + (M // 2) * 8      # 12 587 008
 ALGO_BYTES_WIRE = M * N * 12 + (M // 2) * 8        # 6 295 552
-WORKLOAD = "default sector 1024x512x3 (rpv2.cu:38-45), batch of sectors, fused chain"
+WORKLOAD = ("default sector 1024x512x3 (rpv2.cu:38-45), all stages fused; one step = one 360-degree PPI "
+            "elevation of 143 sectors (rpv2.cu:39 n_sectors) per GPU")
 
 
 def load_peaks():
@@ -337,8 +338,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sectors", type=int, default=64, help="sectors per GPU per step (HBM-resident leg)")
-    ap.add_argument("--e2e-sectors", type=int, default=64, help="sectors per GPU per step (host leg)")
+    ap.add_argument("--sectors", type=int, default=143, help="sectors per GPU per step (HBM-resident leg)")
+    ap.add_argument("--e2e-sectors", type=int, default=143, help="sectors per GPU per step (host leg)")
     ap.add_argument("--host-piece", type=int, default=8, help="sectors per pinned-ring piece")
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=0)

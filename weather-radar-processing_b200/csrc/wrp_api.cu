@@ -398,6 +398,14 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->x2_lag, h->ctrl, h->smax, h->fused, M, N,
                                              C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, h->l2_window, st));
                 h->launches++;
+                if (const char *dbg = getenv("WRP_DEBUG")) {
+                    if (atoi(dbg) & 16) {
+                        int na = 0, nb = 0;
+                        cudaStreamSynchronize(st);
+                        wrp::persistent_debug_counters(h->ctrl, &na, &nb);
+                        fprintf(stderr, "[wrp debug] %d sectors: dependency unmet at probe: %d range tiles, %d Doppler blocks\n", S, na, nb);
+                    }
+                }
             } else {
                 {
                     ProfScope ps(h, st, 1);

@@ -126,6 +126,8 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
                               float calib, float taps_sum, int sm_count, size_t l2_window_bytes, cudaStream_t st);
 
+void persistent_debug_counters(const int *ctrl, int *not_ready_a, int *not_ready_b);
+
 // Staged path (wrp_staged.cu): the reference cascade, one stage per kernel.
 // Returns the number of kernels launched through *launches.
 cudaError_t staged_setup();

@@ -119,6 +119,8 @@ struct PersistParams {
     int ring, lag;
     int tiles_a, blocks_b, pair_blocks;
     int tile_bytes;
+    int bulk_piece;
+    int b_async; // Doppler blocks loaded with cp.async instead of bulk copies
     int debug; // WRP_DEBUG bisect switches (development only)
     int n1, n2, n3, b3_first; // queue regions (see decode_item)
     int total_items;
@@ -227,14 +229,47 @@ __device__ __forceinline__ void issue_load_b(const Item &it, const PersistParams
         const int g0 = it.sub * (rows / 2);
         const uint8_t *hh = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
         const uint8_t *vv = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 1) * p.half_m + g0) * row_bytes;
-        bulk_load(buf, hh, TILE_BYTES / 2, bar);
-        bulk_load(buf + TILE_BYTES / 2, vv, TILE_BYTES / 2, bar);
+        const int piece = p.bulk_piece; // bytes per bulk request (several requests pipeline in the TMA unit)
+        for (int o = 0; o < TILE_BYTES / 2; o += piece) {
+            bulk_load(buf + o, hh + o, piece, bar);
+            bulk_load(buf + TILE_BYTES / 2 + o, vv + o, piece, bar);
+        }
     } else {
         const int g0 = (it.sub - p.pair_blocks) * rows;
         const int ch = p.C == 1 ? 0 : 2;
         const uint8_t *src = (const uint8_t *)p.x2 + (((size_t)slot * p.C + ch) * p.half_m + g0) * row_bytes;
-        bulk_load(buf, src, TILE_BYTES, bar);
+        const int piece = p.bulk_piece;
+        for (int o = 0; o < TILE_BYTES; o += piece) bulk_load(buf + o, src + o, piece, bar);
     }
+}
+
+// Doppler block through cp.async (all threads): same bytes as issue_load_b, more requests in flight
+template <int T>
+__device__ __forceinline__ void issue_load_b_async(const Item &it, const PersistParams &p, uint8_t *buf,
+                                                   uint64_t *bar, int tid)
+{
+    constexpr int TILE_BYTES = T * 8192, THREADS = 32 * T;
+    const int slot = it.sector % p.ring;
+    const size_t row_bytes = (size_t)p.N * sizeof(float2);
+    const int rows = TILE_BYTES / (int)row_bytes;
+    const uint8_t *s0, *s1;
+    if (it.sub < p.pair_blocks) {
+        const int g0 = it.sub * (rows / 2);
+        s0 = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 0) * p.half_m + g0) * row_bytes;
+        s1 = (const uint8_t *)p.x2 + (((size_t)slot * p.C + 1) * p.half_m + g0) * row_bytes;
+    } else {
+        const int g0 = (it.sub - p.pair_blocks) * rows;
+        const int ch = p.C == 1 ? 0 : 2;
+        s0 = (const uint8_t *)p.x2 + (((size_t)slot * p.C + ch) * p.half_m + g0) * row_bytes;
+        s1 = s0 + TILE_BYTES / 2;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int o = (tid + k * THREADS) * 16;
+        cp_async16(buf + o, s0 + o);
+        cp_async16(buf + TILE_BYTES / 2 + o, s1 + o);
+    }
+    cp_async_arrive(bar);
 }
 
 // Range tile (all threads): 1024 rows x T*8 B, 16 B per cp.async (a warp covers 512 contiguous-row bytes).
@@ -308,6 +343,9 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         if (it.kind == 0) {
             __syncthreads();
             issue_load_a<N, T>(it, p, tile, &mbar_a, tid);
+        } else if (p.b_async) {
+            __syncthreads();
+            issue_load_b_async<T>(it, p, tile, &mbar_a, tid);
         } else if (tid == 0) {
             issue_load_b(it, p, tile, &mbar_b);
         }
@@ -325,7 +363,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         int claimed = 0;
         int4 nx = make_int4(-1, 0, 0, 1);
         if (tid == 0) claimed = atomicAdd(p.ctrl, 1);
-        if (it.kind == 0) {
+        if (it.kind == 0 || p.b_async) {
             mbar_wait(&mbar_a, phase_a);
             phase_a ^= 1;
         } else {
@@ -407,6 +445,8 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             if (nit.kind >= 0 && ready) {
                 if (nit.kind == 0)
                     issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
+                else if (p.b_async)
+                    issue_load_b_async<T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
                     issue_load_b(nit, p, tile, &mbar_b);
             }
@@ -491,6 +531,8 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             if (nit.kind >= 0 && ready) {
                 if (nit.kind == 0)
                     issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
+                else if (p.b_async)
+                    issue_load_b_async<T>(nit, p, tile, &mbar_a, tid);
                 else if (tid == 0)
                     issue_load_b(nit, p, tile, &mbar_b);
             }
@@ -550,6 +592,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         }
         // the probe found the next item's dependency unmet: this CTA's own item is signalled
         // (or about to be, by its other warps), so a blocking wait is safe now
+        if ((p.debug & 16) && tid == 0 && nit.kind >= 0 && !ready) atomicAdd(p.ctrl + 1 + nit.kind, 1);
         if (nit.kind < 0 || !ready) {
             // leaving the loop, or about to block on a dependency: publish the pending tile first
             // (the item waited for may be this CTA's own).  nit and ready are CTA-uniform.
@@ -563,6 +606,9 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 if (nit.kind == 0) {
                     __syncthreads();
                     issue_load_a<N, T>(nit, p, tile, &mbar_a, tid);
+                } else if (p.b_async) {
+                    __syncthreads();
+                    issue_load_b_async<T>(nit, p, tile, &mbar_a, tid);
                 } else if (tid == 0) {
                     issue_load_b(nit, p, tile, &mbar_b);
                 }
@@ -638,6 +684,9 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.b3_first = S > L ? S - L : 0;
     p.total_items = S * (p.tiles_a + p.blocks_b);
     p.smax = smax;
+    p.bulk_piece = getenv("WRP_BULK_PIECE") ? atoi(getenv("WRP_BULK_PIECE")) : p.tile_bytes / 2;
+    if (p.bulk_piece < 512 || (p.tile_bytes / 2) % p.bulk_piece) p.bulk_piece = p.tile_bytes / 2;
+    p.b_async = getenv("WRP_B_ASYNC") ? atoi(getenv("WRP_B_ASYNC")) : 0;
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
     p.calib = calib;
@@ -680,6 +729,15 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     }
     cfg.dynamicSmemBytes = Tables<32, 4>::SMEM;
     return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 4>, p);
+}
+
+// development aid (WRP_DEBUG=16): how many queue items found their dependency unmet when probed
+void persistent_debug_counters(const int *ctrl, int *not_ready_a, int *not_ready_b)
+{
+    int v[3] = {0, 0, 0};
+    cudaMemcpy(v, ctrl, sizeof v, cudaMemcpyDeviceToHost);
+    *not_ready_a = v[1];
+    *not_ready_b = v[2];
 }
 
 } // namespace wrp
