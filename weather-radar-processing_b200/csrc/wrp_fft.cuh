@@ -87,13 +87,33 @@ template <int R> __host__ __device__ constexpr int brev(int i)
     return r;
 }
 
+// Packed complex add/sub: one sm_100 FADD2 on the (re, im) register pair instead of two FADDs.
+// Same FP32 throughput (measured: tools/micro/ffma2.cu), half the issue slots — and the chain is
+// issue-bound.  ptxas keeps float2 values in aligned pairs, so no moves are added.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
 // One DIT butterfly with twiddle w = exp(SIGN * 2*pi*i * T/32): (a, b) <- (a + w b, a - w b).
 template <int T, int SIGN> __device__ __forceinline__ void bfly(float2 &a, float2 &b)
 {
     if constexpr (T == 0) {
         const float2 t = b;
-        b = make_float2(a.x - t.x, a.y - t.y);
-        a = make_float2(a.x + t.x, a.y + t.y);
+        b = csub(a, t);
+        a = cadd(a, t);
     } else if constexpr (T == 8) {
         // w = SIGN * i
         const float2 t = SIGN > 0 ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);

@@ -686,7 +686,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.smax = smax;
     p.bulk_piece = getenv("WRP_BULK_PIECE") ? atoi(getenv("WRP_BULK_PIECE")) : p.tile_bytes / 2;
     if (p.bulk_piece < 512 || (p.tile_bytes / 2) % p.bulk_piece) p.bulk_piece = p.tile_bytes / 2;
-    p.b_async = getenv("WRP_B_ASYNC") ? atoi(getenv("WRP_B_ASYNC")) : 0;
+    p.b_async = getenv("WRP_B_ASYNC") ? atoi(getenv("WRP_B_ASYNC")) : 1; // +1 % over bulk copies
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
     p.calib = calib;
