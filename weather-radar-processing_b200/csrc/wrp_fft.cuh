@@ -107,6 +107,24 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b)
     return *reinterpret_cast<float2 *>(&d);
 }
 
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) // element-wise (a.x*b.x, a.y*b.y), one FMUL2
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 c) // element-wise a*b + c, one FFMA2
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
 // One DIT butterfly with twiddle w = exp(SIGN * 2*pi*i * T/32): (a, b) <- (a + w b, a - w b).
 template <int T, int SIGN> __device__ __forceinline__ void bfly(float2 &a, float2 &b)
 {

@@ -132,7 +132,7 @@ constexpr int CTRL_A = 32;
 // dependency counters invalidate L1)
 // rows are padded by 16 B so that the 128-bit reads of lanes holding different rows hit
 // different banks
-constexpr int WRC_ROW = 32 * 4 + 16;   // wr(i)*c transposed [32][32] float
+constexpr int WRC_ROW = 32 * 8 + 16;   // wr(i)*c transposed [32][32], each value stored twice (w, w) for FMUL2
 constexpr int TWA_ROW = 32 * 8 + 16;   // range inter-pass twiddles [32][32] float2
 constexpr int TAB_WRC = 32 * WRC_ROW;
 constexpr int TAB_TWA = 32 * TWA_ROW;
@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     __ldg(reinterpret_cast<const float4 *>(src) + i);
             }
         };
-        copy_rows(Tab::OFF_WRC, p.wrc_t, 32, 32 * 4, WRC_ROW);
+        for (int i = tid; i < 32 * 32; i += THREADS) { // window values duplicated into (w, w) pairs
+            const float w = __ldg(p.wrc_t + i);
+            *reinterpret_cast<float2 *>(tile + Tab::OFF_WRC + (i >> 5) * WRC_ROW + (i & 31) * 8) = make_float2(w, w);
+        }
         copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
         copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
         copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
@@ -386,20 +389,21 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage:
                 // the span-1 partners of the bit-reversed network are rows a and a + 16
                 const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
+                const float2 wd2 = make_float2(wdj, wdj), m2 = make_float2(-2.f, -2.f);
                 const float4 *w4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_WRC + b * WRC_ROW);
-                static_for<R / 8>([&](auto qi) {
+                static_for<R / 4>([&](auto qi) { // two rows a, a+1 per 128-bit table read
                     constexpr int q = decltype(qi)::value;
-                    const float4 wlo = w4[q], whi = w4[q + R / 8];
-                    const float wl[4] = {wlo.x * wdj, wlo.y * wdj, wlo.z * wdj, wlo.w * wdj};
-                    const float wh[4] = {whi.x * wdj, whi.y * wdj, whi.z * wdj, whi.w * wdj};
-                    static_for<4>([&](auto ei) {
+                    const float4 wlo = w4[q], whi = w4[q + R / 4];
+                    static_for<2>([&](auto ei) {
                         constexpr int e = decltype(ei)::value;
-                        constexpr int sa = brev<R>(4 * q + e); // even slot; its partner row a + R/2 sits in sa + 1
-                        static_assert(brev<R>(4 * q + e + R / 2) == sa + 1, "span-1 partner");
-                        const float2 A = v[sa], B = v[sa + 1];
-                        const float tx = B.x * wh[e], ty = B.y * wh[e];
-                        v[sa] = make_float2(fmaf(A.x, wl[e], tx), fmaf(A.y, wl[e], ty));
-                        v[sa + 1] = make_float2(fmaf(A.x, wl[e], -tx), fmaf(A.y, wl[e], -ty));
+                        constexpr int sa = brev<R>(2 * q + e); // even slot; partner row a + R/2 sits in sa + 1
+                        static_assert(brev<R>(2 * q + e + R / 2) == sa + 1, "span-1 partner");
+                        const float2 wl = cmul2(e ? make_float2(wlo.z, wlo.w) : make_float2(wlo.x, wlo.y), wd2);
+                        const float2 wh = cmul2(e ? make_float2(whi.z, whi.w) : make_float2(whi.x, whi.y), wd2);
+                        const float2 t = cmul2(v[sa + 1], wh);
+                        const float2 s2 = cfma2(v[sa], wl, t); // A*wl + B*wh
+                        v[sa + 1] = cfma2(t, m2, s2);          // A*wl - B*wh
+                        v[sa] = s2;
                     });
                 });
             }
@@ -539,16 +543,14 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             fft_dit<32, +1>(u);
             // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
             // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
-            float pw = 0.f;
-            static_for<32>([&](auto ki) {
+            if (ka >= R1B - 2) u[15] = make_float2(0.f, 0.f); // the two clipped bins
+            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            static_for<32>([&](auto ki) { // (sum re^2, sum im^2) with one FFMA2 per bin
                 constexpr int kb = decltype(ki)::value;
-                const float e = fmaf(u[kb].x, u[kb].x, u[kb].y * u[kb].y);
-                if (kb == 15) {
-                    if (ka < R1B - 2) pw += e;
-                } else {
-                    pw += e;
-                }
+                acc[kb & 3] = cfma2(u[kb], u[kb], acc[kb & 3]);
             });
+            const float2 a2 = cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3]));
+            float pw = a2.x + a2.y;
 #pragma unroll
             for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
             pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
