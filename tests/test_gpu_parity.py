@@ -331,3 +331,33 @@ def test_cpp_radar_processor_cli(wrp, oracle, sectors, refs, tmp_path):
         want = refs[0].stages[name][0]
         den = np.abs(want).max(axis=0 if st == "02fft1" else -1, keepdims=True)
         assert np.max(np.abs(got - want) / den) <= 1e-4, st
+
+
+def test_fused_path_1024_pulse_dwell(wrp, oracle):
+    """The stress dwell N = 1024 (BASELINE config 5's Doppler length) through the fused persistent
+    kernel (radix-32 x radix-32 Doppler), all three channels, against the oracle."""
+    n = 1024
+    secs = [wrp.synth.make_sector_int16(M, n, s, 1) for s in range(2)]
+    data = np.stack([wrp.synth.to_planar(x) for x in secs])
+    with wrp.RadarChain(0, n_cols_N=n) as ch:
+        out = ch.process_host(data, 2)
+    for s in range(2):
+        ref = oracle.chain(data[s].astype(np.complex128))
+        assert_products_close(out[s], ref.zdb, ref.zdr, f"N=1024 sector {s}")
+
+
+def test_stress_shape_4096x1024_staged(wrp, oracle):
+    """BASELINE config 5 shape (4x range gates, 1024-pulse dwell, dual-pol): M = 4096 is served by the
+    generic staged cascade (the fused kernels are specialised for M = 1024) and must still match."""
+    m, n, c = 4096, 1024, 2
+    iq16 = wrp.synth.make_sector_int16(m, n, 2, 0)
+    x = wrp.synth.to_planar(iq16, c)
+    with pytest.raises(wrp.WrpError) as ei:
+        wrp.RadarChain(0, n_rows_M=m, n_cols_N=n, n_channels=c)  # fused mode: unsupported shape, says so
+    assert ei.value.status == 2
+    with wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=1, n_rows_M=m, n_cols_N=n, n_channels=c) as ch:
+        out = ch.process_host(x[None], 1)[0]
+        p_hh = ch.dump_stage("power", 0, 0).astype(np.float64)
+    ref = oracle.chain(x.astype(np.complex128), dumps=True)
+    assert_products_close(out, ref.zdb, ref.zdr, "4096x1024")
+    assert rel_l2(p_hh, ref.stages["power"][0]) < 1e-5
