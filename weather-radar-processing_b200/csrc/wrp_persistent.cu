@@ -120,6 +120,7 @@ struct PersistParams {
     int tiles_a, blocks_b, pair_blocks;
     int tile_bytes;
     int bulk_piece;
+    int dephase_ns;
     int b_async; // Doppler blocks loaded with cp.async instead of bulk copies
     int debug; // WRP_DEBUG bisect switches (development only)
     int n1, n2, n3, b3_first; // queue regions (see decode_item)
@@ -329,6 +330,9 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
     }
     if (p.debug & 1) return;
+    // experiment: de-phase the two CTAs of an SM (they start together and items are equal-length)
+    if (p.dephase_ns > 0 && blockIdx.x >= gridDim.x / 2)
+        for (int t = 0; t < p.dephase_ns; t += 500) __nanosleep(500);
     int pending = -1; // sector whose range tile this CTA finished but has not signalled yet
     if (tid == 0) {
         mbar_init(&mbar_a, THREADS);
@@ -689,6 +693,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.bulk_piece = getenv("WRP_BULK_PIECE") ? atoi(getenv("WRP_BULK_PIECE")) : p.tile_bytes / 2;
     if (p.bulk_piece < 512 || (p.tile_bytes / 2) % p.bulk_piece) p.bulk_piece = p.tile_bytes / 2;
     p.b_async = getenv("WRP_B_ASYNC") ? atoi(getenv("WRP_B_ASYNC")) : 1; // +1 % over bulk copies
+    p.dephase_ns = getenv("WRP_DEPHASE_NS") ? atoi(getenv("WRP_DEPHASE_NS")) : 0;
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
     p.calib = calib;
