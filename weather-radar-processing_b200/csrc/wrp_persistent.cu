@@ -1,0 +1,693 @@
+// wrp_persistent.cu — the fused chain as ONE persistent kernel per batch (sm_100a).
+//
+// Work items, handed out in queue order by an atomic counter:
+//   A(s, tile)  range tile: T (= 8) adjacent columns x 1024 rows of one (sector, channel) plane.
+//               cp.async (16 B, L1 bypass) -> window folded into the first butterfly stage ->
+//               radix-32 x radix-32 column FFT with an in-place shared-memory exchange -> rows
+//               k < M/2 to the x2 ring (stages 01-02; replaces __apply_hamming + the strided cuFFT
+//               plan, rpv2.cu:86-91, 318-333, 418-428).
+//   B(s, block) Doppler block: 16 rows (8 gates x hh,vv or 16 gates of vh) of the x2 ring ->
+//               mean removal, inverse DFT, shift, clip, |.|^2, moving-average power, ZdB/ZDR
+//               (stages 03-10; replaces rpv2.cu:93-213, 434-566).  Rows are warp-private.
+// The queue interleaves A(t) with B(t - lag), so the x2 hand-off lives in a small ring
+// (ring x 6 MiB) that never leaves L2, there is no kernel boundary between the phases, and
+// DRAM-heavy A items overlap compute-heavy B items on every SM.
+//
+// Synchronisation inside a CTA.  The 64 KiB tile buffer is cut into one 8 KiB region per warp;
+// the last shared-memory reads of an item (second FFT pass) touch only the warp's own region for
+// BOTH item kinds, and the next item's bytes for that region are fetched by that warp.  So a warp
+// prefetches the moment it has pulled its own operands — no buffer-release barrier — and loads
+// overlap the second pass and the epilogue.  An mbarrier (one arrival per thread, fired by
+// cp.async completion) tells everybody when the whole next tile has landed.  The only CTA barrier
+// left is the range tile's exchange between its two FFT passes; Doppler blocks have none.
+// Thread 0 claims the next queue slot at the top of an item, decodes and probes it mid-item and
+// publishes it through shared memory (sequence counters, no barrier).
+//
+// Cross-CTA ordering: per-sector completion counters.  A warp publishes its share of a finished
+// range tile with red.release.gpu later on (after the first pass of its next item, when the
+// stores have long drained); Doppler blocks are only loaded once their sector's count is full
+// (ld.relaxed.gpu probe; data is then read with cp.async.cg straight from L2).  An item only waits
+// for items earlier in the queue, and nobody spins while holding unpublished work: no deadlock.
+#include <cstdlib>
+
+#include "wrp_fft.cuh"
+#include "wrp_internal.h"
+
+namespace wrp {
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 16-byte async copy global -> shared (L1 bypass).  An L2 evict-first cache hint was tried here
+// (cp.async ... .L2::cache_hint): ptxas 12.9 allocated an odd uniform register for the LDGSTS
+// descriptor at one call site and the warp trapped with "illegal instruction"; st/ld
+// eviction-priority qualifiers need 256-bit vectors on sm_100.  WRP_L2_PERSIST pins the ring instead.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// arrive on `bar` once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// producer/consumer named barrier: warps that only announce do not wait
+__device__ __forceinline__ void bar_arrive(int id, int threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// release-add: orders the executing thread's prior writes and, through the preceding __syncwarp,
+// its warp's (cumulativity); no L1 invalidation, unlike __threadfence()
+__device__ __forceinline__ void red_release_add(int *p)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+// probe without the L1 invalidate an acquire load carries: the counter is bumped by a release
+// (data is in L2 before the count moves) and everything read under it is fetched by cp.async.cg
+// straight from L2, issued after the value has been seen
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const int *p, int target)
+{
+    while (ld_acquire(p) < target) __nanosleep(100);
+}
+
+// ---- parameters ----------------------------------------------------------------------------
+struct PersistParams {
+    const float *wrc_t;
+    const float *wd;
+    const float2 *tw_a;
+    const float2 *tw_b;
+    const float2 *iq; // input [S][C][M][N]
+    float2 *x2;       // ring [ring][C][M/2][N]
+    float *out;       // [S][M/2][2]
+    float *power;     // optional [S][C][M/2]
+    int *ctrl;        // [0] work counter; [1..2] debug; a_done at CTRL_A; b_done at CTRL_A + smax
+    int S, C, N, half_m;
+    int ring, lag;
+    int tiles_a, blocks_b, pair_blocks;
+    int n1, n2, n3, b3_first; // queue regions (see decode_item)
+    int total_items;
+    int smax;
+    int debug; // WRP_DEBUG development switches
+    float range_res, calib, taps_sum;
+};
+constexpr int CTRL_A = 32;
+// shared-memory copies of the small tables; rows are padded by 16 B so that the 128-bit reads of
+// lanes holding different rows hit different banks
+constexpr int WRC_ROW = 32 * 8 + 16; // wr(i)*c transposed [32][32], each value stored twice (w, w) for FMUL2
+constexpr int TWA_ROW = 32 * 8 + 16; // range inter-pass twiddles [32][32] float2
+constexpr int TAB_WRC = 32 * WRC_ROW;
+constexpr int TAB_TWA = 32 * TWA_ROW;
+// T = columns per range tile = warps per CTA; the tile buffer holds T*8 KiB, 8 KiB per warp
+template <int R1B, int T> struct Tables {
+    static constexpr int TILE_BYTES = T * 8192;
+    static constexpr int N = 32 * R1B;
+    static constexpr int TWB_ROW = R1B * 8 + 16; // Doppler inter-pass twiddles [32][R1B] float2
+    static constexpr int WD = N * 4;             // Doppler window
+    static constexpr int TWB = 32 * TWB_ROW;
+    static constexpr int OFF_WRC = TILE_BYTES;
+    static constexpr int OFF_TWA = OFF_WRC + TAB_WRC;
+    static constexpr int OFF_TWB = OFF_TWA + TAB_TWA;
+    static constexpr int OFF_WD = OFF_TWB + TWB;
+    static constexpr int SMEM = OFF_WD + WD;
+};
+
+struct Item {
+    int kind; // 0 = range tile, 1 = Doppler block, < 0 = queue empty
+    int sector;
+    int sub;
+};
+
+// queue: n1 steps of [A]; n2 steps of [A, B]; n3 steps of [B]
+__device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
+{
+    Item it;
+    const int TA = p.tiles_a, TB = p.blocks_b;
+    if (idx < p.n1 * TA) {
+        it.kind = 0;
+        it.sector = idx / TA;
+        it.sub = idx - it.sector * TA;
+        return it;
+    }
+    idx -= p.n1 * TA;
+    const int per = TA + TB;
+    if (idx < p.n2 * per) {
+        const int t = idx / per, r = idx - t * per;
+        if (r < TA) {
+            it.kind = 0;
+            it.sector = p.n1 + t;
+            it.sub = r;
+        } else {
+            it.kind = 1;
+            it.sector = t;
+            it.sub = r - TA;
+        }
+        return it;
+    }
+    idx -= p.n2 * per;
+    it.kind = 1;
+    const int t = idx / TB;
+    it.sector = p.b3_first + t;
+    it.sub = idx - t * TB;
+    return it;
+}
+
+// dependency of an item: the counter it must see reach `target` before its copy may start
+//   range tile of sector s >= ring: WAR on ring slot — the Doppler blocks of sector s - ring must
+//                                   have pulled their rows;
+//   Doppler block of sector s:      every range tile of sector s has been published.
+template <int T> __device__ __forceinline__ const int *item_dep(const Item &it, const PersistParams &p, int &target)
+{
+    if (it.kind == 0) {
+        target = p.blocks_b;
+        return it.sector >= p.ring ? p.ctrl + CTRL_A + p.smax + (it.sector - p.ring) : nullptr;
+    }
+    target = p.tiles_a;
+    return p.ctrl + CTRL_A + it.sector;
+}
+
+// The executing warp fetches its own 8 KiB region of the item's tile (16 cp.async per lane).
+//   range tile:    rows [1024/T * warp, +1024/T) of the T-column tile (16-byte chunks, T/2 per row)
+//   Doppler block: the warp's RPW rows of the x2 ring, contiguous N*8 bytes each
+template <int N, int T>
+__device__ __forceinline__ void issue_warp_load(const Item &it, const PersistParams &p, uint8_t *tile, uint64_t *bar,
+                                                int warp, int lane)
+{
+    uint8_t *dst = tile + warp * 8192 + lane * 16;
+    if (it.kind == 0) {
+        constexpr int tiles_per_plane = N / T, CPR = T / 2, RPWARP = 1024 / T;
+        const int ch = it.sub / tiles_per_plane, col_tile = it.sub - ch * tiles_per_plane;
+        const uint8_t *src = (const uint8_t *)p.iq +
+                             ((size_t)(it.sector * p.C + ch) * 1024 + warp * RPWARP + lane / CPR) * (N * 8) +
+                             col_tile * (T * 8) + (lane % CPR) * 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8));
+    } else {
+        constexpr int ROWS_B = T * 1024 / N, RPW = ROWS_B / T;
+        const int slot = it.sector % p.ring;
+        const bool pair = it.sub < p.pair_blocks;
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            // row (warp, rr) -> (channel, gate): see the Doppler epilogue
+            int chn, gate;
+            if (pair) {
+                chn = RPW == 2 ? rr : (warp & 1);
+                gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
+            } else {
+                chn = p.C == 1 ? 0 : 2;
+                gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rr;
+            }
+            const uint8_t *src =
+                (const uint8_t *)p.x2 + (((size_t)slot * p.C + chn) * p.half_m + gate) * (size_t)(N * 8) + lane * 16;
+#pragma unroll
+            for (int k = 0; k < 16 / RPW; ++k) cp_async16(dst + rr * (N * 8) + k * 512, src + k * 512);
+        }
+    }
+    cp_async_arrive(bar);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+template <int R1B, int T> // Doppler length N = 32 * R1B; T columns per range tile = warps per CTA
+__global__ void __launch_bounds__(32 * T, 16 / T)
+    chain_persistent_kernel(const PersistParams p)
+{
+    constexpr int R = 32; // range FFT 32 x 32 (M = 1024)
+    constexpr int N = 32 * R1B;
+    constexpr int THREADS = 32 * T;
+    using Tab = Tables<R1B, T>;
+    constexpr int PITCH = T * 8;         // bytes per range-tile row
+    constexpr int SW = 128 / PITCH - 1;  // row-swizzle mask of the in-place exchange
+    constexpr int ROWS_B = T * 1024 / N; // Doppler rows per block
+    constexpr int RPW = ROWS_B / T;      // rows per warp
+    static_assert(RPW == 1 || RPW == 2, "Doppler rows per warp");
+    extern __shared__ __align__(1024) uint8_t tile[];
+    __shared__ __align__(8) uint64_t mbar; // next tile has landed: one arrival per thread, fired by its cp.asyncs
+    __shared__ int4 s_item[2];             // published items (kind, sector, sub, -)
+    __shared__ volatile int s_seq;         // items published so far
+    __shared__ volatile int s_go;          // items whose dependency is known to be met
+    __shared__ float p_row[ROWS_B];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        // copy the tables into (row-padded) shared memory, 16 B per step
+        auto copy_rows = [&](int off, const void *src, int rows, int row_bytes, int row_pitch) {
+            const int per_row = row_bytes / 16;
+            for (int i = tid; i < rows * per_row; i += THREADS) {
+                const int r = i / per_row, q = i - r * per_row;
+                *reinterpret_cast<float4 *>(tile + off + r * row_pitch + q * 16) =
+                    __ldg(reinterpret_cast<const float4 *>(src) + i);
+            }
+        };
+        for (int i = tid; i < 32 * 32; i += THREADS) { // window values duplicated into (w, w) pairs
+            const float w = __ldg(p.wrc_t + i);
+            *reinterpret_cast<float2 *>(tile + Tab::OFF_WRC + (i >> 5) * WRC_ROW + (i & 31) * 8) = make_float2(w, w);
+        }
+        copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
+        copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
+        copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
+    }
+    int claimed_next = 0; // thread 0: queue index of the item after the current one (claimed one item ahead)
+    if (tid == 0) {
+        mbar_init(&mbar, THREADS);
+        const int first = atomicAdd(p.ctrl, 1);
+        claimed_next = atomicAdd(p.ctrl, 1);
+        Item f{-1, 0, 0};
+        if (first < p.total_items) {
+            f = decode_item(first, p);
+            int target;
+            const int *dep = item_dep<T>(f, p, target);
+            if (dep) spin_until(dep, target); // nothing is held yet: blocking is safe
+        }
+        s_item[0] = make_int4(f.kind, f.sector, f.sub, 0);
+        s_seq = 1;
+        s_go = 1;
+    }
+    __syncthreads();
+    Item it{s_item[0].x, s_item[0].y, s_item[0].z};
+    if (it.kind >= 0) issue_warp_load<N, T>(it, p, tile, &mbar, warp, lane);
+
+    uint32_t phase = 0;
+    int n = 0;        // index of the current item in this CTA's sequence
+    int pending = -1; // sector of a finished range tile whose completion this CTA has not published yet
+    // One release per tile per CTA without a blocking CTA barrier: every warp but warp 0 only
+    // announces (bar.arrive) that it is past the tile's stores; warp 0 waits for the announcements
+    // (bar.sync) and its lane 0 publishes.  `pending` is CTA-uniform (same item sequence in all warps).
+    auto publish_pending = [&]() {
+        if (pending >= 0) {
+            if (warp == 0) {
+                bar_sync(1, THREADS);
+                if (lane == 0) red_release_add(p.ctrl + CTRL_A + pending);
+            } else {
+                bar_arrive(1, THREADS);
+            }
+            pending = -1;
+        }
+    };
+
+    while (it.kind >= 0) {
+        const int nslot = (n + 1) & 1;
+        Item nit{-1, 0, 0};
+        bool loaded = false;
+        // Thread 0 works one item ahead: the queue slot of item n+1 was claimed during item n-1, so
+        // it can be decoded and its dependency probed right now; the claim for item n+2 goes out at
+        // the same time.  Both round trips hide behind this item's first pass; the results are
+        // published (shared memory, no barrier) right after it.
+        Item cand{-1, 0, 0};
+        int probe = 0, probe_target = 0, claimed_next2 = 0;
+        const int *probe_dep = nullptr;
+        if (tid == 0) {
+            if (claimed_next < p.total_items) {
+                cand = decode_item(claimed_next, p);
+                probe_dep = item_dep<T>(cand, p, probe_target);
+                probe = probe_dep ? ld_relaxed(probe_dep) : (probe_target = 0);
+            }
+            claimed_next2 = atomicAdd(p.ctrl, 1);
+        }
+        auto publish_next = [&]() {
+            if (tid == 0) {
+                bool ready = probe >= probe_target;
+                if (!ready) ready = ld_relaxed(probe_dep) >= probe_target; // the early probe may be stale
+                if ((p.debug & 16) && cand.kind >= 0 && !ready) atomicAdd(p.ctrl + 1 + cand.kind, 1);
+                s_item[nslot] = make_int4(cand.kind, cand.sector, cand.sub, 0);
+                if (ready) s_go = n + 2; // before s_seq: whoever sees the item also sees that it may load
+                __threadfence_block();
+                s_seq = n + 2;
+                claimed_next = claimed_next2;
+            }
+        };
+        // a warp that has pulled its last operand out of its region learns the next item and, if
+        // that item's dependency is already met, starts fetching its own region of it
+        auto prefetch_next = [&]() {
+            while (s_seq < n + 2) {
+            }
+            nit = Item{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z};
+            if (nit.kind >= 0 && s_go >= n + 2) {
+                issue_warp_load<N, T>(nit, p, tile, &mbar, warp, lane);
+                loaded = true;
+            }
+        };
+
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+
+        if (it.kind == 0) {
+            // ================= range tile =================
+            const int c = tid % T, b = tid / T;
+            constexpr int tiles_per_plane = N / T;
+            const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * T + c;
+            float2 v[R];
+            {
+                const uint8_t *src = tile + b * PITCH + c * 8;
+                static_for<R>([&](auto ai) {
+                    constexpr int a = decltype(ai)::value;
+                    v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
+                });
+                // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage:
+                // the span-1 partners of the bit-reversed network are rows a and a + 16
+                const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
+                const float2 wd2 = make_float2(wdj, wdj), m2 = make_float2(-2.f, -2.f);
+                const float4 *w4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_WRC + b * WRC_ROW);
+                static_for<R / 4>([&](auto qi) { // two rows a, a+1 per 128-bit table read
+                    constexpr int q = decltype(qi)::value;
+                    const float4 wlo = w4[q], whi = w4[q + R / 4];
+                    static_for<2>([&](auto ei) {
+                        constexpr int e = decltype(ei)::value;
+                        constexpr int sa = brev<R>(2 * q + e); // even slot; partner row a + R/2 sits in sa + 1
+                        static_assert(brev<R>(2 * q + e + R / 2) == sa + 1, "span-1 partner");
+                        const float2 wl = cmul2(e ? make_float2(wlo.z, wlo.w) : make_float2(wlo.x, wlo.y), wd2);
+                        const float2 wh = cmul2(e ? make_float2(whi.z, whi.w) : make_float2(whi.x, whi.y), wd2);
+                        const float2 t = cmul2(v[sa + 1], wh);
+                        const float2 s2 = cfma2(v[sa], wl, t); // A*wl + B*wh
+                        v[sa + 1] = cfma2(t, m2, s2);          // A*wl - B*wh
+                        v[sa] = s2;
+                    });
+                });
+            }
+            fft_dit_after_stage1<R, -1>(v);
+            publish_pending();
+            publish_next();
+            __syncwarp();
+            {
+                // Z[ka][b] goes to row 32 ka + (b ^ (ka & SW)): the warp keeps its own row footprint
+                // (in place), and the 128/PITCH values of ka met by one shared-memory wavefront of
+                // pass 2 fall into different PITCH-byte slices of a 128-byte bank line
+                const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWA + b * TWA_ROW);
+                uint8_t *d_sw[SW + 1];
+#pragma unroll
+                for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = tile + (b ^ sx) * PITCH + c * 8;
+                static_for<R / 2>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = t4[q];
+                    const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                    const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                    *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
+                    *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
+                });
+            }
+            __syncthreads(); // the exchange: the one CTA barrier of a range tile
+            const int ka = b; // rows 32 ka + .. of warp w (ka = 32/T * w ..) are its own 8 KiB region
+            {
+                const uint32_t off_sw = (uint32_t)(ka * (R * PITCH) + c * 8) | (uint32_t)((ka & SW) * PITCH);
+                static_for<R>([&](auto bi) {
+                    constexpr int bb = decltype(bi)::value;
+                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(tile + (off_sw ^ (uint32_t)(bb * PITCH)));
+                });
+            }
+            __syncwarp();
+            prefetch_next();
+            fft_dit<R, -1>(v);
+            {
+                float2 *out = p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m + ka) * (size_t)N + col;
+                static_for<R / 2>([&](auto ki) { // rows k = ka + 32 kb < M/2
+                    constexpr int kb = decltype(ki)::value;
+                    out[(size_t)(R * kb) * N] = v[kb];
+                });
+            }
+            pending = it.sector; // published later (release), when these stores have drained
+        } else {
+            // ================= Doppler block =================
+            if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1); // ring rows are in smem now
+            const bool pair = it.sub < p.pair_blocks;
+            uint8_t *region = tile + warp * 8192; // rows (warp, rr) live at region + rr * N*8
+            {
+                float2 tw[R1B];
+                const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWB + lane * Tab::TWB_ROW);
+                static_for<R1B / 2>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = t4[q];
+                    tw[2 * q] = make_float2(w.x, w.y);
+                    tw[2 * q + 1] = make_float2(w.z, w.w);
+                });
+#pragma unroll 1
+                for (int rr = 0; rr < RPW; ++rr) {
+                    uint8_t *row = region + rr * (N * 8);
+                    float2 v[R1B];
+                    static_for<R1B>([&](auto ai) {
+                        constexpr int a = decltype(ai)::value;
+                        v[brev<R1B>(a)] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
+                    });
+                    fft_dit<R1B, +1>(v);
+                    // mean removal (rpv2.cu:93-130): only the a-sum (ka = 0) carries the row mean
+                    float sx = v[0].x, sy = v[0].y;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                    }
+                    v[0].x -= sx * (1.f / 32.f);
+                    v[0].y -= sy * (1.f / 32.f);
+                    __syncwarp();
+                    // Z_l[ka] -> float2 index 32 ka + (l ^ ((ka & 7) << 1)): 16-byte chunks of group ka
+                    // are XOR-swizzled so pass 2's 128-bit reads are conflict-free
+                    static_for<R1B>([&](auto ki) {
+                        constexpr int ka = decltype(ki)::value;
+                        const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
+                        *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
+                    });
+                }
+            }
+            publish_pending();
+            publish_next();
+            __syncwarp();
+            float2 u[32];
+            const int rsel = RPW == 2 ? (lane >> 4) : 0;
+            const int ka = RPW == 2 ? (lane & 15) : lane;
+            {
+                const uint8_t *grp = region + rsel * (N * 8) + ka * 256;
+                const int sw = (ka & 7) * 16;
+                static_for<16>([&](auto ci) {
+                    constexpr int cc = decltype(ci)::value;
+                    const float4 q = *reinterpret_cast<const float4 *>(grp + ((cc * 16) ^ sw));
+                    u[brev<32>(2 * cc)] = make_float2(q.x, q.y);
+                    u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
+                });
+            }
+            __syncwarp();
+            prefetch_next();
+            fft_dit<32, +1>(u);
+            // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
+            // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
+            if (ka >= R1B - 2) u[15] = make_float2(0.f, 0.f); // the two clipped bins
+            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            static_for<32>([&](auto ki) { // (sum re^2, sum im^2) with one FFMA2 per bin
+                constexpr int kb = decltype(ki)::value;
+                acc[kb & 3] = cfma2(u[kb], u[kb], acc[kb & 3]);
+            });
+            const float2 a2 = cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3]));
+            float pw = a2.x + a2.y;
+#pragma unroll
+            for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+            pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
+            // (channel, gate) of this thread's row — the same map issue_warp_load uses
+            int chn, gate;
+            if (pair) {
+                chn = RPW == 2 ? rsel : (warp & 1);
+                gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
+            } else {
+                chn = p.C == 1 ? 0 : 2;
+                gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rsel;
+            }
+            if (p.power && ka == 0) p.power[((size_t)it.sector * p.C + chn) * p.half_m + gate] = pw;
+            if constexpr (RPW == 2) {
+                // stages 09/10 (rpv2.cu:199-213): hh in the low half-warp, vv in the high one
+                const float other = __shfl_xor_sync(0xffffffffu, pw, 16);
+                if ((pair && lane == 0) || (!pair && p.C == 1 && ka == 0)) {
+                    const float rg = (float)gate * p.range_res;
+                    const float z = rg * rg * p.calib * pw;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + gate] =
+                        make_float2(10.f * log10f(z), pair ? 10.f * (log10f(pw) - log10f(other)) : 0.f);
+                }
+            } else {
+                // N = 1024: one row per warp, (hh, vv) of a gate sit in neighbouring warps
+                if (lane == 0) p_row[warp] = pw;
+                __syncthreads();
+                if (lane == 0 && ((pair && !(warp & 1)) || (!pair && p.C == 1))) {
+                    const float rg = (float)gate * p.range_res;
+                    const float z = rg * rg * p.calib * pw;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)it.sector * p.half_m + gate] =
+                        make_float2(10.f * log10f(z), pair ? 10.f * (log10f(pw) - log10f(p_row[warp + 1])) : 0.f);
+                }
+                __syncthreads();
+            }
+        }
+
+        if (nit.kind < 0) {
+            publish_pending(); // leaving: nothing may stay unpublished
+        } else if (!loaded) {
+            // the next item's dependency was unmet when probed.  Publish what this warp still holds
+            // (the item waited for may be this CTA's own), then thread 0 waits for the counter and
+            // releases everybody through shared memory.
+            publish_pending();
+            if (tid == 0) {
+                int target;
+                const int *dep = item_dep<T>(nit, p, target);
+                if (dep) spin_until(dep, target);
+                s_go = n + 2;
+            }
+            while (s_go < n + 2) {
+            }
+            issue_warp_load<N, T>(nit, p, tile, &mbar, warp, lane);
+        }
+        it = nit;
+        ++n;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+bool persistent_supported(int M, int N) { return M == 1024 && (N == 512 || N == 1024); }
+int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
+
+static int tile_cols()
+{
+    static int t = 0;
+    if (!t) {
+        const char *env = getenv("WRP_TILE_COLS");
+        t = env && atoi(env) == 4 ? 4 : 8; // 8 columns (64-byte row segments) measured 24 % faster than 4
+    }
+    return t;
+}
+
+cudaError_t persistent_setup()
+{
+    cudaError_t e;
+#define WRP_SET(R1B, T)                                                                                      \
+    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                             Tables<R1B, T>::SMEM);                                                          \
+    if (e != cudaSuccess) return e;
+    WRP_SET(16, 8)
+    WRP_SET(16, 4)
+    WRP_SET(32, 8)
+    WRP_SET(32, 4)
+#undef WRP_SET
+    return cudaSuccess;
+}
+
+// One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
+cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
+                              int *ctrl, int smax, const FusedTables &t, int M, int N, int C, int n_sectors,
+                              float range_res, float calib, float taps_sum, int sm_count, size_t l2_window_bytes,
+                              cudaStream_t st)
+{
+    if (n_sectors == 0) return cudaSuccess;
+    if (!persistent_supported(M, N) || n_sectors > smax || ring < lag + 2) return cudaErrorInvalidValue;
+    const int T = tile_cols();
+
+    PersistParams p{};
+    p.wrc_t = t.wrc_t;
+    p.wd = t.wd;
+    p.tw_a = t.tw_a;
+    p.tw_b = t.tw_b;
+    p.iq = iq;
+    p.x2 = x2_ring;
+    p.out = out;
+    p.power = power;
+    p.ctrl = ctrl;
+    p.S = n_sectors;
+    p.C = C;
+    p.N = N;
+    p.half_m = M / 2;
+    p.ring = ring;
+    p.lag = lag;
+    const int rows_b = T * 1024 / N;
+    p.tiles_a = (N / T) * C;
+    p.pair_blocks = C >= 2 ? (M / 2) / (rows_b / 2) : 0;
+    p.blocks_b = p.pair_blocks + ((C & 1) ? (M / 2) / rows_b : 0);
+    const int L = p.lag, S = n_sectors;
+    p.n1 = S < L ? S : L;
+    p.n2 = S > L ? S - L : 0;
+    p.n3 = S < L ? S : L;
+    p.b3_first = S > L ? S - L : 0;
+    p.total_items = S * (p.tiles_a + p.blocks_b);
+    p.smax = smax;
+    p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
+    p.range_res = range_res;
+    p.calib = calib;
+    p.taps_sum = taps_sum;
+
+    cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
+    if (e != cudaSuccess) return e;
+    int grid = (16 / T) * sm_count;
+    if (grid > p.total_items) grid = p.total_items;
+
+    // Optional (WRP_L2_PERSIST=1, which also carves persisting L2 out at wrp_create): pin the x2
+    // ring in L2 for this launch through an access-policy window, so the streamed input cannot push
+    // the hand-off rows out to DRAM.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * T);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int n_attr = 0;
+    if (l2_window_bytes > 0) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = (void *)x2_ring;
+        attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n_attr = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    if (N == 512 && T == 8) {
+        cfg.dynamicSmemBytes = Tables<16, 8>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 8>, p);
+    } else if (N == 512) {
+        cfg.dynamicSmemBytes = Tables<16, 4>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 4>, p);
+    } else if (T == 8) {
+        cfg.dynamicSmemBytes = Tables<32, 8>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 8>, p);
+    }
+    cfg.dynamicSmemBytes = Tables<32, 4>::SMEM;
+    return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 4>, p);
+}
+
+// development aid (WRP_DEBUG=16): how many queue items found their dependency unmet when probed
+void persistent_debug_counters(const int *ctrl, int *not_ready_a, int *not_ready_b)
+{
+    int v[3] = {0, 0, 0};
+    cudaMemcpy(v, ctrl, sizeof v, cudaMemcpyDeviceToHost);
+    *not_ready_a = v[1];
+    *not_ready_b = v[2];
+}
+
+} // namespace wrp
