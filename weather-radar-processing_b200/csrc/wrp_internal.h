@@ -81,8 +81,8 @@ struct wrp_handle {
     int chunk = 1;
     // persistent form: x2 is a ring of `ring` sector slots; ctrl holds the work/dependency counters
     bool persistent = false;
-    int x2_ring = 7; // sector slots of the x2 hand-off ring
-    int x2_lag = 3;  // Doppler blocks of sector t are queued after the range tiles of sector t + lag
+    int x2_ring = 8; // sector slots of the x2 hand-off ring (50 MB, L2-resident)
+    int x2_lag = 4;  // Doppler blocks of sector t are queued after the range tiles of sector t + lag
     int *ctrl = nullptr;
     int smax = 1024; // sectors per persistent launch
     size_t l2_window = 0; // bytes of the x2 ring pinned in L2 per launch (0 = off)

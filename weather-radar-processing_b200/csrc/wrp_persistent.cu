@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 });
             }
             fft_dit_after_stage1<R, -1>(v);
+            publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
             publish_pending();
-            publish_next();
             __syncwarp();
             {
                 // Z[ka][b] goes to row 32 ka + (b ^ (ka & SW)): the warp keeps its own row footprint
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     });
                 }
             }
+            publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
             publish_pending();
-            publish_next();
             __syncwarp();
             float2 u[32];
             const int rsel = RPW == 2 ? (lane >> 4) : 0;
