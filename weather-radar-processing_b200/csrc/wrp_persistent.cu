@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 if (ready) s_go = n + 2; // before s_seq: whoever sees the item also sees that it may load
                 __threadfence_block();
                 s_seq = n + 2;
-                claimed_next = claimed_next2;
             }
         };
         // a warp that has pulled its last operand out of its region learns the next item and, if
@@ -568,6 +567,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
         }
         it = nit;
         ++n;
+        claimed_next = claimed_next2; // consumed at the next item's top: the atomic has long returned
     }
 }
 
