@@ -1,4 +1,8 @@
-// wrp_fused.cu — the fused fast path: two kernels per chunk of sectors.
+// wrp_fused.cu — v1 of the fused path (two kernels per chunk of sectors) and the wire decoder.
+//
+// The product path is the persistent kernel in wrp_persistent.cu; this two-kernel form is kept for
+// A/B measurements (WRP_FUSED_IMPL=v1: 109 k sectors/s against 216 k) and as the simplest statement
+// of the two fused stages:
 //
 //   range_fft_kernel   stage 01 (window on load) + stage 02 (range FFT along i), writing
 //                      only the rows k < M/2 that survive stage 04 (rpv2.cu:502).
@@ -13,7 +17,7 @@
 //                      FFT pair, __apply_ma, __scale_real, __sum_inplace_v4 and
 //                      __calcresult_v2 (rpv2.cu:93-213, 434-566).
 //   decode_wire_kernel wire records -> planar complex float (sector.cpp:52-62 +
-//                      rpv2.cu:369-383) for WRP_FMT_WIRE_I16BE input.
+//                      rpv2.cu:369-383) for WRP_FMT_WIRE_I16BE input (used by both forms).
 //
 // Both FFT kernels are two-pass Cooley-Tukey with in-register radix-16/32 passes
 // (wrp_fft.cuh) and one shared-memory exchange; loads are straight global->register,
