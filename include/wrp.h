@@ -111,7 +111,7 @@ typedef struct {
     size_t input_bytes_per_sector;  /* in the configured input_fmt                       */
     size_t output_floats_per_sector; /* 2 * M/2                                          */
     size_t intermediate_bytes_per_sector; /* range->Doppler hand-off kept in L2          */
-    int chunk_sectors;              /* sectors per kernel pair (sized to stay L2-resident) */
+    int chunk_sectors;              /* sectors per launch (persistent kernel) or per kernel pair (v1) */
     int kernels_per_chunk;          /* launches of our kernels per chunk                 */
 } wrp_info;
 

@@ -361,3 +361,28 @@ def test_stress_shape_4096x1024_staged(wrp, oracle):
     ref = oracle.chain(x.astype(np.complex128), dumps=True)
     assert_products_close(out, ref.zdb, ref.zdr, "4096x1024")
     assert rel_l2(p_hh, ref.stages["power"][0]) < 1e-5
+
+
+def test_large_batch_is_deterministic_and_order_independent(wrp, sectors, refs):
+    """A batch several times the x2 ring (so range tiles wait for Doppler blocks to release ring
+    slots and Doppler blocks wait for range tiles): results must not depend on scheduling — two
+    runs are bit-identical and every sector equals its single-sector result."""
+    torch = pytest.importorskip("torch")
+    n = 40
+    planar = [wrp.synth.to_planar(x) for x in sectors]
+    batch = np.stack([planar[(i * 7) % 3] for i in range(n)])
+    d_in = torch.from_numpy(batch.view(np.float32).reshape(-1)).cuda()
+    d_out = torch.zeros((n, M // 2, 2), device="cuda")
+    with wrp.RadarChain(0) as ch:
+        ch.process_device(d_in.data_ptr(), n, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        a = d_out.cpu().numpy().copy()
+        d_out.zero_()
+        ch.process_device(d_in.data_ptr(), n, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        b = d_out.cpu().numpy()
+        single = ch.process_host(np.stack(planar), 3)
+    assert np.array_equal(a, b)
+    for i in range(n):
+        assert np.array_equal(a[i], single[(i * 7) % 3]), f"sector {i}"
+        assert_products_close(a[i], refs[(i * 7) % 3].zdb, refs[(i * 7) % 3].zdr, f"sector {i}")
