@@ -36,6 +36,7 @@ $(CSRC)/wrp_tables.o: $(CSRC)/wrp_tables.cpp $(CSRC)/wrp_internal.h include/wrp.
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+	python tools/check_sass.py $@
 
 oracle:
 	$(MAKE) -C oracle liboracle.so

@@ -158,8 +158,14 @@ static int create_impl(wrp_handle *h)
                     size_t want = inter * h->x2_ring;
                     if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
                     if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
-                    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-                        h->l2_window = want;
+                    cudaError_t le = cudaErrorInvalidValue;
+                    if (want > 0) le = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                    if (le == cudaSuccess) h->l2_window = want;
+                    if (getenv("WRP_DEBUG"))
+                        fprintf(stderr, "[wrp debug] L2 persist: ring %zu B, persistingL2CacheMaxSize %d, "
+                                        "accessPolicyMaxWindowSize %d, window %zu, setLimit: %s\n",
+                                inter * h->x2_ring, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize,
+                                h->l2_window, cudaGetErrorString(le));
                     cudaGetLastError();
                 }
             }

@@ -69,6 +69,22 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// Same copy with an L2 evict-first policy: the input is streamed once and should not push the x2
+// ring out of L2.  (With an earlier code shape ptxas 12.9 gave one call site an ODD uniform
+// descriptor register for this instruction form and the warp trapped with "illegal instruction";
+// tools/check_sass.py fails the build if that ever comes back.)
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_evict_first(void *dst, const void *src, uint64_t pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
+                 "l"(pol)
+                 : "memory");
+}
 // arrive on `bar` once every cp.async this thread has issued so far has landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
 {
@@ -126,6 +142,8 @@ struct PersistParams {
     int n1, n2, n3, b3_first; // queue regions (see decode_item)
     int total_items;
     int smax;
+    int evict_first; // stream the input through L2 with an evict-first policy (WRP_EVICT_FIRST=0 turns it off)
+    int discard; // drop consumed ring rows from L2 with discard.global.L2 (WRP_DISCARD=1 turns it on)
     int debug; // WRP_DEBUG development switches
     float range_res, calib, taps_sum;
 };
@@ -204,6 +222,29 @@ template <int T> __device__ __forceinline__ const int *item_dep(const Item &it, 
     return p.ctrl + CTRL_A + it.sector;
 }
 
+// x2-ring address of row (warp, rr) of a Doppler block, and its (channel, gate)
+template <int N, int T>
+__device__ __forceinline__ const uint8_t *doppler_row(const Item &it, const PersistParams &p, int warp, int rr,
+                                                      int &chn, int &gate)
+{
+    constexpr int ROWS_B = T * 1024 / N, RPW = ROWS_B / T;
+    if (it.sub < p.pair_blocks) {
+        chn = RPW == 2 ? rr : (warp & 1);
+        gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
+    } else {
+        chn = p.C == 1 ? 0 : 2;
+        gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rr;
+    }
+    const int slot = it.sector % p.ring;
+    return (const uint8_t *)p.x2 + (((size_t)slot * p.C + chn) * p.half_m + gate) * (size_t)(N * 8);
+}
+// The ring rows are scratch: once a Doppler block has them in shared memory their L2 lines are
+// dropped, so the dirty lines are never written back to DRAM
+__device__ __forceinline__ void discard_l2_line(const void *p)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 // The executing warp fetches its own 8 KiB region of the item's tile (16 cp.async per lane).
 //   range tile:    rows [1024/T * warp, +1024/T) of the T-column tile (16-byte chunks, T/2 per row)
 //   Doppler block: the warp's RPW rows of the x2 ring, contiguous N*8 bytes each
@@ -218,25 +259,23 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
         const uint8_t *src = (const uint8_t *)p.iq +
                              ((size_t)(it.sector * p.C + ch) * 1024 + warp * RPWARP + lane / CPR) * (N * 8) +
                              col_tile * (T * 8) + (lane % CPR) * 16;
+        // (N = 512 instances only: in the spilling N = 1024 instances ptxas picks an odd descriptor
+        // register for the hinted form — see cp_async16_evict_first)
+        if (N == 512 && p.evict_first) {
+            const uint64_t pol = policy_evict_first();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8));
+            for (int k = 0; k < 16; ++k)
+                cp_async16_evict_first(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8), pol);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8));
+        }
     } else {
         constexpr int ROWS_B = T * 1024 / N, RPW = ROWS_B / T;
-        const int slot = it.sector % p.ring;
-        const bool pair = it.sub < p.pair_blocks;
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
-            // row (warp, rr) -> (channel, gate): see the Doppler epilogue
             int chn, gate;
-            if (pair) {
-                chn = RPW == 2 ? rr : (warp & 1);
-                gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
-            } else {
-                chn = p.C == 1 ? 0 : 2;
-                gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rr;
-            }
-            const uint8_t *src =
-                (const uint8_t *)p.x2 + (((size_t)slot * p.C + chn) * p.half_m + gate) * (size_t)(N * 8) + lane * 16;
+            const uint8_t *src = doppler_row<N, T>(it, p, warp, rr, chn, gate) + lane * 16;
 #pragma unroll
             for (int k = 0; k < 16 / RPW; ++k) cp_async16(dst + rr * (N * 8) + k * 512, src + k * 512);
         }
@@ -306,19 +345,25 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
 
     uint32_t phase = 0;
     int n = 0;        // index of the current item in this CTA's sequence
-    int pending = -1; // sector of a finished range tile whose completion this CTA has not published yet
-    // One release per tile per CTA without a blocking CTA barrier: every warp but warp 0 only
-    // announces (bar.arrive) that it is past the tile's stores; warp 0 waits for the announcements
-    // (bar.sync) and its lane 0 publishes.  `pending` is CTA-uniform (same item sequence in all warps).
+    int pending = -1;   // sector of a finished range tile whose completion this CTA has not published yet
+    int pending_b = -1; // sector of a Doppler block whose ring rows were consumed (and discarded) but not yet reported
+    // One release per item per CTA without a blocking CTA barrier: every warp but warp 0 only
+    // announces (bar.arrive) that it is past the stores / discards in question; warp 0 waits for
+    // the announcements (bar.sync) and its lane 0 publishes.  Both variables are CTA-uniform (all
+    // warps walk the same item sequence).
     auto publish_pending = [&]() {
-        if (pending >= 0) {
+        if (pending >= 0 || pending_b >= 0) {
             if (warp == 0) {
                 bar_sync(1, THREADS);
-                if (lane == 0) red_release_add(p.ctrl + CTRL_A + pending);
+                if (lane == 0) {
+                    if (pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
+                    if (pending_b >= 0) red_release_add(p.ctrl + CTRL_A + p.smax + pending_b);
+                }
             } else {
                 bar_arrive(1, THREADS);
             }
             pending = -1;
+            pending_b = -1;
         }
     };
 
@@ -443,7 +488,22 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             pending = it.sector; // published later (release), when these stores have drained
         } else {
             // ================= Doppler block =================
-            if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1); // ring rows are in smem now
+            // the ring rows are in shared memory now: drop their L2 lines (never written back), then
+            // tell the range tiles that will reuse the ring slot — after every warp's discards
+            if (p.discard) {
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) {
+                    int chn_, gate_;
+                    const uint8_t *row_g = doppler_row<N, T>(it, p, warp, rr, chn_, gate_);
+#pragma unroll
+                    for (int k = 0; k < (N * 8) / (128 * 32); ++k) discard_l2_line(row_g + (k * 32 + lane) * 128);
+                }
+            }
+            if (!p.discard) {
+                if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1);
+            } else {
+                pending_b = it.sector; // reported after this item's first pass, when the discards have drained
+            }
             const bool pair = it.sub < p.pair_blocks;
             uint8_t *region = tile + warp * 8192; // rows (warp, rr) live at region + rr * N*8
             {
@@ -515,15 +575,9 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
 #pragma unroll
             for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
             pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
-            // (channel, gate) of this thread's row — the same map issue_warp_load uses
+            // (channel, gate) of this thread's row — the same map the loads use
             int chn, gate;
-            if (pair) {
-                chn = RPW == 2 ? rsel : (warp & 1);
-                gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
-            } else {
-                chn = p.C == 1 ? 0 : 2;
-                gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rsel;
-            }
+            (void)doppler_row<N, T>(it, p, warp, rsel, chn, gate);
             if (p.power && ka == 0) p.power[((size_t)it.sector * p.C + chn) * p.half_m + gate] = pw;
             if constexpr (RPW == 2) {
                 // stages 09/10 (rpv2.cu:199-213): hh in the low half-warp, vv in the high one
@@ -637,6 +691,8 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.b3_first = S > L ? S - L : 0;
     p.total_items = S * (p.tiles_a + p.blocks_b);
     p.smax = smax;
+    p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : 1;
+    p.discard = getenv("WRP_DISCARD") ? atoi(getenv("WRP_DISCARD")) : 0; // -2 % throughput; evict-first already keeps the ring in L2
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
     p.calib = calib;
