@@ -380,6 +380,22 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
     const int M = c.n_rows_M, N = c.n_cols_N, C = c.n_channels;
     const size_t in_bytes = input_bytes_per_sector(c);
     const size_t out_floats = (size_t)M; // 2 * M/2
+    if (c.mode == WRP_MODE_FUSED && h->persistent && c.input_fmt == WRP_FMT_WIRE_I16BE && n_sectors > h->chunk &&
+        h->chunk < 64) {
+        // a large HBM-resident wire batch: grow the decode scratch (up to 64 sectors) so that the
+        // persistent kernel gets launches long enough to amortise its ramp-up and tail
+        const int want = n_sectors < 64 ? n_sectors : 64;
+        CK(h, cudaStreamSynchronize(st));
+        CK(h, cudaDeviceSynchronize());
+        float2 *bigger = nullptr;
+        if (cudaMalloc((void **)&bigger, (size_t)want * C * M * N * sizeof(float2)) == cudaSuccess) {
+            cudaFree(h->decoded);
+            h->decoded = bigger;
+            h->chunk = want;
+        } else {
+            cudaGetLastError(); // keep the small scratch
+        }
+    }
     for (int s0 = 0; s0 < n_sectors; s0 += h->chunk) {
         const int S = n_sectors - s0 < h->chunk ? n_sectors - s0 : h->chunk;
         const uint8_t *in = (const uint8_t *)dev_iq + (size_t)s0 * in_bytes;
