@@ -21,7 +21,7 @@ from . import dumpio, synth  # noqa: F401  (re-exported helpers)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libwrp.so")
+LIB_PATH = os.environ.get("WRP_LIB") or os.path.join(_HERE, "libwrp.so")  # WRP_LIB: A/B builds in experiments
 
 WRP_OK = 0
 FMT_C64_PLANAR = 0

@@ -457,9 +457,13 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 uint8_t *d_sw[SW + 1];
 #pragma unroll
                 for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = tile + (b ^ sx) * PITCH + c * 8;
+                // the twiddle reads run two steps ahead of the exchange stores: both go to the same
+                // shared-memory array, so the compiler will not hoist a load above a store by itself
+                float4 wq[3] = {t4[0], t4[1], t4[2]};
                 static_for<R / 2>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = t4[q];
+                    const float4 w = wq[q % 3];
+                    if constexpr (q + 3 < R / 2) wq[q % 3] = t4[q + 3];
                     const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
                     const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
                     *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
