@@ -347,13 +347,13 @@ def test_fused_path_1024_pulse_dwell(wrp, oracle):
 
 
 def test_stress_shape_4096x1024_staged(wrp, oracle):
-    """BASELINE config 5 shape (4x range gates, 1024-pulse dwell, dual-pol): M = 4096 is served by the
-    generic staged cascade (the fused kernels are specialised for M = 1024) and must still match."""
+    """BASELINE config 5 shape (4x range gates, 1024-pulse dwell, dual-pol) through the generic staged
+    cascade; shapes the fused kernel is not built for (M = 2048) are refused in fused mode, loudly."""
     m, n, c = 4096, 1024, 2
     iq16 = wrp.synth.make_sector_int16(m, n, 2, 0)
     x = wrp.synth.to_planar(iq16, c)
     with pytest.raises(wrp.WrpError) as ei:
-        wrp.RadarChain(0, n_rows_M=m, n_cols_N=n, n_channels=c)  # fused mode: unsupported shape, says so
+        wrp.RadarChain(0, n_rows_M=2048, n_cols_N=n, n_channels=c)  # fused mode: unsupported shape, says so
     assert ei.value.status == 2
     with wrp.RadarChain(0, mode=wrp.MODE_STAGED, max_batch=1, n_rows_M=m, n_cols_N=n, n_channels=c) as ch:
         out = ch.process_host(x[None], 1)[0]
@@ -361,6 +361,33 @@ def test_stress_shape_4096x1024_staged(wrp, oracle):
     ref = oracle.chain(x.astype(np.complex128), dumps=True)
     assert_products_close(out, ref.zdb, ref.zdr, "4096x1024")
     assert rel_l2(p_hh, ref.stages["power"][0]) < 1e-5
+    with wrp.RadarChain(0, max_batch=1, n_rows_M=m, n_cols_N=n, n_channels=c) as ch:
+        fused = ch.process_host(x[None], 1)[0]
+    assert_products_close(fused, out[:, 0].astype(np.float64), out[:, 1].astype(np.float64), "fused vs staged 4096x1024")
+
+
+@pytest.mark.parametrize("n,c", [(1024, 3), (512, 2), (512, 3), (1024, 1)])
+def test_fused_path_4096_range_gates(wrp, oracle, n, c):
+    """BASELINE config 5 (M = 4096) through the fused persistent kernel: radix-4 pre-pass + four
+    1024-point sub-transforms per column.  Five sectors on a three-slot x2 ring, so range tiles
+    wait for ring slots and Doppler blocks for range tiles; device-resident and host paths agree."""
+    torch = pytest.importorskip("torch")
+    m, S = 4096, 5
+    secs = [wrp.synth.to_planar(wrp.synth.make_sector_int16(m, n, s, 0), c) for s in range(2)]
+    refs = [oracle.chain(x.astype(np.complex128)) for x in secs]
+    batch = np.stack([secs[i % 2] for i in range(S)])
+    d_in = torch.from_numpy(batch.view(np.float32).reshape(-1)).cuda()
+    d_out = torch.zeros((S, m // 2, 2), device="cuda")
+    with wrp.RadarChain(0, n_rows_M=m, n_cols_N=n, n_channels=c, max_batch=1) as ch:
+        assert ch.info.kernels_per_chunk == 1
+        ch.process_device(d_in.data_ptr(), S, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()
+        one = ch.process_host(batch[1:2], 1)
+    assert np.array_equal(one[0], out[1])
+    for i in range(S):
+        assert np.array_equal(out[i], out[i % 2])
+        assert_products_close(out[i], refs[i % 2].zdb, refs[i % 2].zdr, f"4096x{n}x{c} sector {i}")
 
 
 def test_large_batch_is_deterministic_and_order_independent(wrp, sectors, refs):

@@ -79,6 +79,8 @@ static void free_all(wrp_handle *h)
     F(h->fused.wd);
     F(h->fused.tw_a);
     F(h->fused.tw_b);
+    F(h->fused.wr4);
+    F(h->fused.tw4);
     wrp::StagedBuffers &b = h->staged;
     F(b.s00), F(b.s01), F(b.s02), F(b.s03), F(b.s04), F(b.s05), F(b.s06), F(b.s07), F(b.s08);
     F(b.rowsum), F(b.power), F(b.result), F(b.ham), F(b.fft_ma), F(b.tw_m), F(b.tw_n_fwd), F(b.tw_n_inv);
@@ -116,16 +118,28 @@ static int create_impl(wrp_handle *h)
     if (c.mode == WRP_MODE_FUSED) {
         // transposed window [b][a] = wr_c[32 a + b]; inter-pass twiddles [b][ka] (range) and
         // [l][ka] (Doppler)
-        const int R1a = 32, R2a = M / 32, R1b = N / 32;
-        std::vector<float> wrc_t((size_t)M);
-        std::vector<float> tw_a(2 * (size_t)M), tw_b(2 * (size_t)N);
+        // (M = 4096: the kernel's radix-4 pre-pass leaves 1024-point sub-transforms, whose 32 x 32
+        // twiddles are every 4th entry of the 4096-point table; the window is applied in the pre-pass)
+        const int QM = M / 1024, R1a = 32, R2a = 32, R1b = N / 32;
+        std::vector<float> wrc_t(1024);
+        std::vector<float> tw_a(2 * 1024), tw_b(2 * (size_t)N);
         for (int b = 0; b < R2a; b++)
             for (int a = 0; a < R1a; a++) {
                 wrc_t[(size_t)b * R1a + a] = t.wr_c[R2a * a + b];
-                const int q = (b * a) % M; // ka = a
+                const int q = ((b * a) % 1024) * QM; // ka = a
                 tw_a[2 * ((size_t)b * R1a + a)] = t.tw_m[2 * q];
                 tw_a[2 * ((size_t)b * R1a + a) + 1] = t.tw_m[2 * q + 1];
             }
+        if (QM == 4) {
+            std::vector<float> tw4(2 * 3 * 1024);
+            for (int k = 1; k <= 3; k++)
+                for (int r = 0; r < 1024; r++) {
+                    tw4[2 * ((size_t)(k - 1) * 1024 + r)] = t.tw_m[2 * (r * k)];
+                    tw4[2 * ((size_t)(k - 1) * 1024 + r) + 1] = t.tw_m[2 * (r * k) + 1];
+                }
+            CK(h, upload(&h->fused.wr4, t.wr_c.data(), (size_t)M * 4));
+            CK(h, upload(&h->fused.tw4, tw4.data(), tw4.size() * 4));
+        }
         for (int l = 0; l < 32; l++)
             for (int ka = 0; ka < R1b; ka++) {
                 const int q = (l * ka) % N;
@@ -141,8 +155,16 @@ static int create_impl(wrp_handle *h)
         const size_t inter = (size_t)C * hmn * sizeof(float2);
         const char *impl = getenv("WRP_FUSED_IMPL");
         h->persistent = !(impl && strcmp(impl, "v1") == 0) && wrp::persistent_supported(M, N);
+        if (!h->persistent && !wrp::fused_supported(M, N)) {
+            h->err = "wrp_create: the two-kernel form (WRP_FUSED_IMPL=v1) supports M=1024 only";
+            return WRP_ERR_UNSUPPORTED;
+        }
         if (h->persistent) {
             // x2 hand-off = ring of sector slots that stays in L2 (ring * C*(M/2)*N*8 bytes)
+            if (M == 4096) { // 24-48 MiB of hand-off per sector: keep as few sectors in flight as the queue allows
+                h->x2_lag = 1;
+                h->x2_ring = 3;
+            }
             if (const char *env = getenv("WRP_RING")) h->x2_ring = atoi(env);
             if (const char *env = getenv("WRP_LAG")) h->x2_lag = atoi(env);
             if (h->x2_lag < 1) h->x2_lag = 1;
@@ -239,8 +261,9 @@ int wrp_create(const wrp_config *cfg, int device, wrp_handle **out)
         g_create_error = "wrp_create: M and N must be powers of two in [4, 8192]";
         return WRP_ERR_UNSUPPORTED;
     }
-    if (c.mode == WRP_MODE_FUSED && !wrp::fused_supported(c.n_rows_M, c.n_cols_N)) {
-        g_create_error = "wrp_create: fused mode supports M=1024 with N=512 or 1024; use WRP_MODE_STAGED";
+    if (c.mode == WRP_MODE_FUSED && !wrp::fused_supported(c.n_rows_M, c.n_cols_N) &&
+        !wrp::persistent_supported(c.n_rows_M, c.n_cols_N)) {
+        g_create_error = "wrp_create: fused mode supports M=1024 or 4096 with N=512 or 1024; use WRP_MODE_STAGED";
         return WRP_ERR_UNSUPPORTED;
     }
     int n_dev = 0;

@@ -131,6 +131,8 @@ struct PersistParams {
     const float *wd;
     const float2 *tw_a;
     const float2 *tw_b;
+    const float *wr4;   // M = 4096 only: wr(i)*c, natural order [4096]
+    const float2 *tw4;  // M = 4096 only: exp(-2*pi*i*r*k/4096), [3][1024] for k = 1, 2, 3
     const float2 *iq; // input [S][C][M][N]
     float2 *x2;       // ring [ring][C][M/2][N]
     float *out;       // [S][M/2][2]
@@ -154,15 +156,20 @@ constexpr int WRC_ROW = 32 * 8 + 16; // wr(i)*c transposed [32][32], each value 
 constexpr int TWA_ROW = 32 * 8 + 16; // range inter-pass twiddles [32][32] float2
 constexpr int TAB_WRC = 32 * WRC_ROW;
 constexpr int TAB_TWA = 32 * TWA_ROW;
-// T = columns per range tile = warps per CTA; the tile buffer holds T*8 KiB, 8 KiB per warp
-template <int R1B, int T> struct Tables {
-    static constexpr int TILE_BYTES = T * 8192;
+// T = columns per range tile, Q = M / 1024; T*Q warps per CTA, the tile buffer holds 8 KiB per warp
+template <int R1B, int T, int Q> struct Tables {
+    static constexpr int NW = T * Q;
+    static constexpr int TILE_BYTES = NW * 8192;
     static constexpr int N = 32 * R1B;
     static constexpr int TWB_ROW = R1B * 8 + 16; // Doppler inter-pass twiddles [32][R1B] float2
     static constexpr int WD = N * 4;             // Doppler window
     static constexpr int TWB = 32 * TWB_ROW;
+    // Q = 1: transposed (w, w) window of the fused first stage; Q = 4: wr(i)*c [4096] and the
+    // radix-4 pre-pass twiddles [3][1024]
     static constexpr int OFF_WRC = TILE_BYTES;
-    static constexpr int OFF_TWA = OFF_WRC + TAB_WRC;
+    static constexpr int OFF_W4 = TILE_BYTES;
+    static constexpr int OFF_TW4 = OFF_W4 + 4096 * 4;
+    static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + TAB_WRC : OFF_TW4 + 3 * 1024 * 8;
     static constexpr int OFF_TWB = OFF_TWA + TAB_TWA;
     static constexpr int OFF_WD = OFF_TWB + TWB;
     static constexpr int SMEM = OFF_WD + WD;
@@ -223,11 +230,11 @@ template <int T> __device__ __forceinline__ const int *item_dep(const Item &it, 
 }
 
 // x2-ring address of row (warp, rr) of a Doppler block, and its (channel, gate)
-template <int N, int T>
+template <int N, int NW> // NW = warps per CTA
 __device__ __forceinline__ const uint8_t *doppler_row(const Item &it, const PersistParams &p, int warp, int rr,
                                                       int &chn, int &gate)
 {
-    constexpr int ROWS_B = T * 1024 / N, RPW = ROWS_B / T;
+    constexpr int ROWS_B = NW * 1024 / N, RPW = ROWS_B / NW;
     if (it.sub < p.pair_blocks) {
         chn = RPW == 2 ? rr : (warp & 1);
         gate = it.sub * (ROWS_B / 2) + (RPW == 2 ? warp : (warp >> 1));
@@ -248,7 +255,7 @@ __device__ __forceinline__ void discard_l2_line(const void *p)
 // The executing warp fetches its own 8 KiB region of the item's tile (16 cp.async per lane).
 //   range tile:    rows [1024/T * warp, +1024/T) of the T-column tile (16-byte chunks, T/2 per row)
 //   Doppler block: the warp's RPW rows of the x2 ring, contiguous N*8 bytes each
-template <int N, int T>
+template <int N, int T, int Q>
 __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistParams &p, uint8_t *tile, uint64_t *bar,
                                                 int warp, int lane)
 {
@@ -257,11 +264,11 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
         constexpr int tiles_per_plane = N / T, CPR = T / 2, RPWARP = 1024 / T;
         const int ch = it.sub / tiles_per_plane, col_tile = it.sub - ch * tiles_per_plane;
         const uint8_t *src = (const uint8_t *)p.iq +
-                             ((size_t)(it.sector * p.C + ch) * 1024 + warp * RPWARP + lane / CPR) * (N * 8) +
+                             ((size_t)(it.sector * p.C + ch) * (1024 * Q) + warp * RPWARP + lane / CPR) * (N * 8) +
                              col_tile * (T * 8) + (lane % CPR) * 16;
         // (N = 512 instances only: in the spilling N = 1024 instances ptxas picks an odd descriptor
         // register for the hinted form — see cp_async16_evict_first)
-        if (N == 512 && p.evict_first) {
+        if (p.evict_first) {
             const uint64_t pol = policy_evict_first();
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -271,11 +278,11 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
             for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8));
         }
     } else {
-        constexpr int ROWS_B = T * 1024 / N, RPW = ROWS_B / T;
+        constexpr int NW = T * Q, ROWS_B = NW * 1024 / N, RPW = ROWS_B / NW;
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
             int chn, gate;
-            const uint8_t *src = doppler_row<N, T>(it, p, warp, rr, chn, gate) + lane * 16;
+            const uint8_t *src = doppler_row<N, NW>(it, p, warp, rr, chn, gate) + lane * 16;
 #pragma unroll
             for (int k = 0; k < 16 / RPW; ++k) cp_async16(dst + rr * (N * 8) + k * 512, src + k * 512);
         }
@@ -284,18 +291,24 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <int R1B, int T> // Doppler length N = 32 * R1B; T columns per range tile = warps per CTA
-__global__ void __launch_bounds__(32 * T, 16 / T)
+// Doppler length N = 32 * R1B; T columns per range tile; range length M = 1024 * Q (Q = 1 or 4).
+// Q = 4: a radix-4 decimation-in-frequency pre-pass (window folded in) turns the T columns x 4096
+// rows into 4T independent 1024-point columns, one per warp, whose outputs k' < 512 are the rows
+// 4 k' + k0 < M/2 of the 4096-point transform — so the pruning and both 32 x 32 passes are shared.
+template <int R1B, int T, int Q>
+__global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
     chain_persistent_kernel(const PersistParams p)
 {
-    constexpr int R = 32; // range FFT 32 x 32 (M = 1024)
+    constexpr int R = 32; // (sub-)range FFT 32 x 32
     constexpr int N = 32 * R1B;
-    constexpr int THREADS = 32 * T;
-    using Tab = Tables<R1B, T>;
-    constexpr int PITCH = T * 8;         // bytes per range-tile row
-    constexpr int SW = 128 / PITCH - 1;  // row-swizzle mask of the in-place exchange
-    constexpr int ROWS_B = T * 1024 / N; // Doppler rows per block
-    constexpr int RPW = ROWS_B / T;      // rows per warp
+    constexpr int NW = T * Q; // warps
+    constexpr int THREADS = 32 * NW;
+    using Tab = Tables<R1B, T, Q>;
+    constexpr int PITCH = T * 8;          // bytes per range-tile row
+    constexpr int SW = 128 / PITCH - 1;   // row-swizzle mask of the in-place exchange
+    constexpr int ROWS_B = NW * 1024 / N; // Doppler rows per block
+    constexpr int RPW = ROWS_B / NW;      // rows per warp
+    static_assert(Q == 1 || Q == 4, "range length 1024 or 4096");
     static_assert(RPW == 1 || RPW == 2, "Doppler rows per warp");
     extern __shared__ __align__(1024) uint8_t tile[];
     __shared__ __align__(8) uint64_t mbar; // next tile has landed: one arrival per thread, fired by its cp.asyncs
@@ -315,9 +328,15 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     __ldg(reinterpret_cast<const float4 *>(src) + i);
             }
         };
-        for (int i = tid; i < 32 * 32; i += THREADS) { // window values duplicated into (w, w) pairs
-            const float w = __ldg(p.wrc_t + i);
-            *reinterpret_cast<float2 *>(tile + Tab::OFF_WRC + (i >> 5) * WRC_ROW + (i & 31) * 8) = make_float2(w, w);
+        if constexpr (Q == 1) {
+            for (int i = tid; i < 32 * 32; i += THREADS) { // window values duplicated into (w, w) pairs
+                const float w = __ldg(p.wrc_t + i);
+                *reinterpret_cast<float2 *>(tile + Tab::OFF_WRC + (i >> 5) * WRC_ROW + (i & 31) * 8) =
+                    make_float2(w, w);
+            }
+        } else {
+            copy_rows(Tab::OFF_W4, p.wr4, 1, 4096 * 4, 4096 * 4);
+            copy_rows(Tab::OFF_TW4, p.tw4, 1, 3 * 1024 * 8, 3 * 1024 * 8);
         }
         copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
         copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
     }
     __syncthreads();
     Item it{s_item[0].x, s_item[0].y, s_item[0].z};
-    if (it.kind >= 0) issue_warp_load<N, T>(it, p, tile, &mbar, warp, lane);
+    if (it.kind >= 0) issue_warp_load<N, T, Q>(it, p, tile, &mbar, warp, lane);
 
     uint32_t phase = 0;
     int n = 0;        // index of the current item in this CTA's sequence
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             }
             nit = Item{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z};
             if (nit.kind >= 0 && s_go >= n + 2) {
-                issue_warp_load<N, T>(nit, p, tile, &mbar, warp, lane);
+                issue_warp_load<N, T, Q>(nit, p, tile, &mbar, warp, lane);
                 loaded = true;
             }
         };
@@ -414,16 +433,64 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
 
         if (it.kind == 0) {
             // ================= range tile =================
-            const int c = tid % T, b = tid / T;
+            // Q = 4: thread group `sub` (32 T threads) owns the 1024-row sub-tile k0 = sub
+            const int sub = Q == 1 ? 0 : tid / (32 * T), tl = Q == 1 ? tid : tid % (32 * T);
+            const int c = tl % T, b = tl / T;
             constexpr int tiles_per_plane = N / T;
-            const int ch = it.sub / tiles_per_plane, col = (it.sub - ch * tiles_per_plane) * T + c;
+            const int ch = it.sub / tiles_per_plane, col0 = (it.sub - ch * tiles_per_plane) * T, col = col0 + c;
+            uint8_t *stile = tile + sub * (1024 * PITCH);
+            if constexpr (Q == 4) {
+                // stage 01 + radix-4 DIF step over rows r, r + 1024, r + 2048, r + 3072, in place:
+                //   y_k0[r] = W_4096^(r k0) * sum_q (-i)^(q k0) ham(r + 1024 q) x[r + 1024 q]
+                // one unit = one row r x two adjacent columns (16-byte accesses)
+                constexpr int UNITS = 1024 * T / 2;
+                static_assert(THREADS % (T / 2) == 0, "column pair fixed per thread");
+                const int cp = tid % (T / 2);
+                const float2 wdp = *reinterpret_cast<const float2 *>(tile + Tab::OFF_WD + (col0 + 2 * cp) * 4);
+                const float *wr4 = reinterpret_cast<const float *>(tile + Tab::OFF_W4);
+                const float2 *tw4 = reinterpret_cast<const float2 *>(tile + Tab::OFF_TW4);
+#pragma unroll 2
+                for (int u = tid; u < UNITS; u += THREADS) {
+                    const int r = u / (T / 2);
+                    uint8_t *ptr = tile + r * PITCH + cp * 16;
+                    float4 x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) x[q] = *reinterpret_cast<const float4 *>(ptr + q * (1024 * PITCH));
+                    float2 e[4], o[4]; // even / odd column of the pair
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float w = wr4[r + 1024 * q];
+                        const float wa = w * wdp.x, wb = w * wdp.y;
+                        e[q] = cmul2(make_float2(x[q].x, x[q].y), make_float2(wa, wa));
+                        o[q] = cmul2(make_float2(x[q].z, x[q].w), make_float2(wb, wb));
+                    }
+                    const float2 w1 = tw4[r], w2 = tw4[1024 + r], w3 = tw4[2048 + r];
+                    auto radix4 = [&](float2 (&z)[4]) {
+                        const float2 t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]);
+                        const float2 t2 = cadd(z[1], z[3]), d = csub(z[1], z[3]);
+                        const float2 t3 = make_float2(d.y, -d.x); // -i (x1 - x3)
+                        z[0] = cadd(t0, t2);
+                        z[1] = cmul(cadd(t1, t3), w1);
+                        z[2] = cmul(csub(t0, t2), w2);
+                        z[3] = cmul(csub(t1, t3), w3);
+                    };
+                    radix4(e);
+                    radix4(o);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4 *>(ptr + q * (1024 * PITCH)) = make_float4(e[q].x, e[q].y, o[q].x, o[q].y);
+                }
+                __syncthreads();
+            }
             float2 v[R];
             {
-                const uint8_t *src = tile + b * PITCH + c * 8;
+                const uint8_t *src = stile + b * PITCH + c * 8;
                 static_for<R>([&](auto ai) {
                     constexpr int a = decltype(ai)::value;
                     v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
                 });
+            }
+            if constexpr (Q == 1) {
                 // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage:
                 // the span-1 partners of the bit-reversed network are rows a and a + 16
                 const float wdj = reinterpret_cast<const float *>(tile + Tab::OFF_WD)[col];
@@ -444,8 +511,10 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                         v[sa] = s2;
                     });
                 });
+                fft_dit_after_stage1<R, -1>(v);
+            } else {
+                fft_dit<R, -1>(v);
             }
-            fft_dit_after_stage1<R, -1>(v);
             publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
             publish_pending();
             __syncwarp();
@@ -456,7 +525,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWA + b * TWA_ROW);
                 uint8_t *d_sw[SW + 1];
 #pragma unroll
-                for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = tile + (b ^ sx) * PITCH + c * 8;
+                for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = stile + (b ^ sx) * PITCH + c * 8;
                 // the twiddle reads run two steps ahead of the exchange stores: both go to the same
                 // shared-memory array, so the compiler will not hoist a load above a store by itself
                 float4 wq[3] = {t4[0], t4[1], t4[2]};
@@ -476,17 +545,19 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                 const uint32_t off_sw = (uint32_t)(ka * (R * PITCH) + c * 8) | (uint32_t)((ka & SW) * PITCH);
                 static_for<R>([&](auto bi) {
                     constexpr int bb = decltype(bi)::value;
-                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(tile + (off_sw ^ (uint32_t)(bb * PITCH)));
+                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(stile + (off_sw ^ (uint32_t)(bb * PITCH)));
                 });
             }
             __syncwarp();
             prefetch_next();
             fft_dit<R, -1>(v);
             {
-                float2 *out = p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m + ka) * (size_t)N + col;
-                static_for<R / 2>([&](auto ki) { // rows k = ka + 32 kb < M/2
+                // sub-transform output k' = ka + 32 kb < 512 is row Q k' + sub of the M-point transform
+                float2 *out =
+                    p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m + Q * ka + sub) * (size_t)N + col;
+                static_for<R / 2>([&](auto ki) { // rows k < M/2
                     constexpr int kb = decltype(ki)::value;
-                    out[(size_t)(R * kb) * N] = v[kb];
+                    out[(size_t)(Q * R * kb) * N] = v[kb];
                 });
             }
             pending = it.sector; // published later (release), when these stores have drained
@@ -498,7 +569,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
 #pragma unroll
                 for (int rr = 0; rr < RPW; ++rr) {
                     int chn_, gate_;
-                    const uint8_t *row_g = doppler_row<N, T>(it, p, warp, rr, chn_, gate_);
+                    const uint8_t *row_g = doppler_row<N, NW>(it, p, warp, rr, chn_, gate_);
 #pragma unroll
                     for (int k = 0; k < (N * 8) / (128 * 32); ++k) discard_l2_line(row_g + (k * 32 + lane) * 128);
                 }
@@ -511,14 +582,18 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             const bool pair = it.sub < p.pair_blocks;
             uint8_t *region = tile + warp * 8192; // rows (warp, rr) live at region + rr * N*8
             {
-                float2 tw[R1B];
                 const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWB + lane * Tab::TWB_ROW);
-                static_for<R1B / 2>([&](auto qi) {
-                    constexpr int q = decltype(qi)::value;
-                    const float4 w = t4[q];
-                    tw[2 * q] = make_float2(w.x, w.y);
-                    tw[2 * q + 1] = make_float2(w.z, w.w);
-                });
+                // two rows per warp: the inter-pass twiddles stay in registers across both rows;
+                // one row (N = 1024): they are read as they are used, two steps ahead of the stores
+                float2 tw[RPW == 2 ? R1B : 2];
+                if constexpr (RPW == 2) {
+                    static_for<R1B / 2>([&](auto qi) {
+                        constexpr int q = decltype(qi)::value;
+                        const float4 w = t4[q];
+                        tw[2 * q] = make_float2(w.x, w.y);
+                        tw[2 * q + 1] = make_float2(w.z, w.w);
+                    });
+                }
 #pragma unroll 1
                 for (int rr = 0; rr < RPW; ++rr) {
                     uint8_t *row = region + rr * (N * 8);
@@ -540,11 +615,24 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
                     __syncwarp();
                     // Z_l[ka] -> float2 index 32 ka + (l ^ ((ka & 7) << 1)): 16-byte chunks of group ka
                     // are XOR-swizzled so pass 2's 128-bit reads are conflict-free
-                    static_for<R1B>([&](auto ki) {
-                        constexpr int ka = decltype(ki)::value;
-                        const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
-                        *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
-                    });
+                    if constexpr (RPW == 2) {
+                        static_for<R1B>([&](auto ki) {
+                            constexpr int ka = decltype(ki)::value;
+                            const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
+                            *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
+                        });
+                    } else {
+                        float4 wq[3] = {t4[0], t4[1], t4[2]};
+                        static_for<R1B / 2>([&](auto qi) {
+                            constexpr int q = decltype(qi)::value;
+                            const float4 w = wq[q % 3];
+                            if constexpr (q + 3 < R1B / 2) wq[q % 3] = t4[q + 3];
+                            const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                            const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                            *reinterpret_cast<float2 *>(row + (32 * (2 * q) + (lane ^ (((2 * q) & 7) << 1))) * 8) = y0;
+                            *reinterpret_cast<float2 *>(row + (32 * (2 * q + 1) + (lane ^ (((2 * q + 1) & 7) << 1))) * 8) = y1;
+                        });
+                    }
                 }
             }
             publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
@@ -581,7 +669,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
             // (channel, gate) of this thread's row — the same map the loads use
             int chn, gate;
-            (void)doppler_row<N, T>(it, p, warp, rsel, chn, gate);
+            (void)doppler_row<N, NW>(it, p, warp, rsel, chn, gate);
             if (p.power && ka == 0) p.power[((size_t)it.sector * p.C + chn) * p.half_m + gate] = pw;
             if constexpr (RPW == 2) {
                 // stages 09/10 (rpv2.cu:199-213): hh in the low half-warp, vv in the high one
@@ -621,7 +709,7 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
             }
             while (s_go < n + 2) {
             }
-            issue_warp_load<N, T>(nit, p, tile, &mbar, warp, lane);
+            issue_warp_load<N, T, Q>(nit, p, tile, &mbar, warp, lane);
         }
         it = nit;
         ++n;
@@ -630,30 +718,32 @@ __global__ void __launch_bounds__(32 * T, 16 / T)
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-bool persistent_supported(int M, int N) { return M == 1024 && (N == 512 || N == 1024); }
+bool persistent_supported(int M, int N) { return (M == 1024 || M == 4096) && (N == 512 || N == 1024); }
 int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
 
-static int tile_cols()
+static int tile_cols(int M)
 {
     static int t = 0;
     if (!t) {
         const char *env = getenv("WRP_TILE_COLS");
         t = env && atoi(env) == 4 ? 4 : 8; // 8 columns (64-byte row segments) measured 24 % faster than 4
     }
-    return t;
+    return M == 4096 ? 4 : t; // 4096 rows: 4 columns fill the 128 KiB tile of the 16-warp CTA
 }
 
 cudaError_t persistent_setup()
 {
     cudaError_t e;
-#define WRP_SET(R1B, T)                                                                                      \
-    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                             Tables<R1B, T>::SMEM);                                                          \
+#define WRP_SET(R1B, T, Q)                                                                                   \
+    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             Tables<R1B, T, Q>::SMEM);                                                       \
     if (e != cudaSuccess) return e;
-    WRP_SET(16, 8)
-    WRP_SET(16, 4)
-    WRP_SET(32, 8)
-    WRP_SET(32, 4)
+    WRP_SET(16, 8, 1)
+    WRP_SET(16, 4, 1)
+    WRP_SET(32, 8, 1)
+    WRP_SET(32, 4, 1)
+    WRP_SET(16, 4, 4)
+    WRP_SET(32, 4, 4)
 #undef WRP_SET
     return cudaSuccess;
 }
@@ -666,13 +756,15 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
 {
     if (n_sectors == 0) return cudaSuccess;
     if (!persistent_supported(M, N) || n_sectors > smax || ring < lag + 2) return cudaErrorInvalidValue;
-    const int T = tile_cols();
+    const int T = tile_cols(M), Q = M / 1024, NW = T * Q;
 
     PersistParams p{};
     p.wrc_t = t.wrc_t;
     p.wd = t.wd;
     p.tw_a = t.tw_a;
     p.tw_b = t.tw_b;
+    p.wr4 = t.wr4;
+    p.tw4 = t.tw4;
     p.iq = iq;
     p.x2 = x2_ring;
     p.out = out;
@@ -684,7 +776,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.half_m = M / 2;
     p.ring = ring;
     p.lag = lag;
-    const int rows_b = T * 1024 / N;
+    const int rows_b = NW * 1024 / N;
     p.tiles_a = (N / T) * C;
     p.pair_blocks = C >= 2 ? (M / 2) / (rows_b / 2) : 0;
     p.blocks_b = p.pair_blocks + ((C & 1) ? (M / 2) / rows_b : 0);
@@ -704,7 +796,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
     if (e != cudaSuccess) return e;
-    int grid = (16 / T) * sm_count;
+    int grid = (16 / NW) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
 
     // Optional (WRP_L2_PERSIST=1, which also carves persisting L2 out at wrp_create): pin the x2
@@ -712,7 +804,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     // the hand-off rows out to DRAM.
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(32 * T);
+    cfg.blockDim = dim3(32 * NW);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     int n_attr = 0;
@@ -727,18 +819,20 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     }
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
-    if (N == 512 && T == 8) {
-        cfg.dynamicSmemBytes = Tables<16, 8>::SMEM;
-        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 8>, p);
-    } else if (N == 512) {
-        cfg.dynamicSmemBytes = Tables<16, 4>::SMEM;
-        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<16, 4>, p);
-    } else if (T == 8) {
-        cfg.dynamicSmemBytes = Tables<32, 8>::SMEM;
-        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 8>, p);
+#define WRP_LAUNCH(R1B, TT, QQ)                                                                              \
+    do {                                                                                                     \
+        cfg.dynamicSmemBytes = Tables<R1B, TT, QQ>::SMEM;                                                    \
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ>, p);                            \
+    } while (0)
+    if (Q == 4) {
+        if (N == 512) WRP_LAUNCH(16, 4, 4);
+        WRP_LAUNCH(32, 4, 4);
     }
-    cfg.dynamicSmemBytes = Tables<32, 4>::SMEM;
-    return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<32, 4>, p);
+    if (N == 512 && T == 8) WRP_LAUNCH(16, 8, 1);
+    if (N == 512) WRP_LAUNCH(16, 4, 1);
+    if (T == 8) WRP_LAUNCH(32, 8, 1);
+    WRP_LAUNCH(32, 4, 1);
+#undef WRP_LAUNCH
 }
 
 // development aid (WRP_DEBUG=16): how many queue items found their dependency unmet when probed
