@@ -131,12 +131,7 @@ static int create_impl(wrp_handle *h)
                 tw_a[2 * ((size_t)b * R1a + a) + 1] = t.tw_m[2 * q + 1];
             }
         if (QM == 4) {
-            std::vector<float> tw4(2 * 3 * 1024);
-            for (int k = 1; k <= 3; k++)
-                for (int r = 0; r < 1024; r++) {
-                    tw4[2 * ((size_t)(k - 1) * 1024 + r)] = t.tw_m[2 * (r * k)];
-                    tw4[2 * ((size_t)(k - 1) * 1024 + r) + 1] = t.tw_m[2 * (r * k) + 1];
-                }
+            std::vector<float> tw4(t.tw_m.begin(), t.tw_m.begin() + 2 * 1024); // exp(-2 pi i r / 4096), r < 1024
             CK(h, upload(&h->fused.wr4, t.wr_c.data(), (size_t)M * 4));
             CK(h, upload(&h->fused.tw4, tw4.data(), tw4.size() * 4));
         }

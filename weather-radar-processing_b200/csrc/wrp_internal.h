@@ -32,7 +32,7 @@ struct FusedTables {
     float2 *tw_a = nullptr;  // [R2a][R1a]   exp(-2*pi*i*b*ka/M)    range inter-pass twiddles
     float2 *tw_b = nullptr;  // [32][R1b]    exp(+2*pi*i*l*ka/N)    Doppler inter-pass twiddles
     float *wr4 = nullptr;    // M = 4096: wr_c in natural order (radix-4 pre-pass window)
-    float2 *tw4 = nullptr;   // M = 4096: [3][1024] exp(-2*pi*i*r*k/4096), k = 1..3 (pre-pass twiddles)
+    float2 *tw4 = nullptr;   // M = 4096: [1024] exp(-2*pi*i*r/4096) (pre-pass twiddle)
 };
 
 struct StagedBuffers {

@@ -99,6 +99,10 @@ __device__ __forceinline__ void bar_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+template <int ID> __device__ __forceinline__ void bar_sync_id(int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(threads) : "memory");
+}
 __device__ __forceinline__ int ld_acquire(const int *p)
 {
     int v;
@@ -132,7 +136,7 @@ struct PersistParams {
     const float2 *tw_a;
     const float2 *tw_b;
     const float *wr4;   // M = 4096 only: wr(i)*c, natural order [4096]
-    const float2 *tw4;  // M = 4096 only: exp(-2*pi*i*r*k/4096), [3][1024] for k = 1, 2, 3
+    const float2 *tw4;  // M = 4096 only: exp(-2*pi*i*r/4096), [1024]
     const float2 *iq; // input [S][C][M][N]
     float2 *x2;       // ring [ring][C][M/2][N]
     float *out;       // [S][M/2][2]
@@ -165,11 +169,11 @@ template <int R1B, int T, int Q> struct Tables {
     static constexpr int WD = N * 4;             // Doppler window
     static constexpr int TWB = 32 * TWB_ROW;
     // Q = 1: transposed (w, w) window of the fused first stage; Q = 4: wr(i)*c [4096] and the
-    // radix-4 pre-pass twiddles [3][1024]
+    // radix-4 pre-pass twiddle W^r [1024] (W^2r, W^3r are formed by multiplication)
     static constexpr int OFF_WRC = TILE_BYTES;
     static constexpr int OFF_W4 = TILE_BYTES;
     static constexpr int OFF_TW4 = OFF_W4 + 4096 * 4;
-    static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + TAB_WRC : OFF_TW4 + 3 * 1024 * 8;
+    static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + TAB_WRC : OFF_TW4 + 1024 * 8;
     static constexpr int OFF_TWB = OFF_TWA + TAB_TWA;
     static constexpr int OFF_WD = OFF_TWB + TWB;
     static constexpr int SMEM = OFF_WD + WD;
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             }
         } else {
             copy_rows(Tab::OFF_W4, p.wr4, 1, 4096 * 4, 4096 * 4);
-            copy_rows(Tab::OFF_TW4, p.tw4, 1, 3 * 1024 * 8, 3 * 1024 * 8);
+            copy_rows(Tab::OFF_TW4, p.tw4, 1, 1024 * 8, 1024 * 8);
         }
         copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
         copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                         e[q] = cmul2(make_float2(x[q].x, x[q].y), make_float2(wa, wa));
                         o[q] = cmul2(make_float2(x[q].z, x[q].w), make_float2(wb, wb));
                     }
-                    const float2 w1 = tw4[r], w2 = tw4[1024 + r], w3 = tw4[2048 + r];
+                    const float2 w1 = tw4[r], w2 = cmul(w1, w1), w3 = cmul(w2, w1);
                     auto radix4 = [&](float2 (&z)[4]) {
                         const float2 t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]);
                         const float2 t2 = cadd(z[1], z[3]), d = csub(z[1], z[3]);
@@ -539,7 +543,15 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                     *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
                 });
             }
-            __syncthreads(); // the exchange: the one CTA barrier of a range tile
+            // the exchange: the one barrier of a 1024-point column group (the whole CTA for Q = 1, the
+            // 32 T threads of a sub-tile for Q = 4)
+            if constexpr (Q == 1) __syncthreads();
+            else { // constant barrier ids, so that only 6 of the 16 are reserved
+                if (sub == 0) bar_sync_id<2>(32 * T);
+                else if (sub == 1) bar_sync_id<3>(32 * T);
+                else if (sub == 2) bar_sync_id<4>(32 * T);
+                else bar_sync_id<5>(32 * T);
+            }
             const int ka = b; // rows 32 ka + .. of warp w (ka = 32/T * w ..) are its own 8 KiB region
             {
                 const uint32_t off_sw = (uint32_t)(ka * (R * PITCH) + c * 8) | (uint32_t)((ka & SW) * PITCH);
@@ -728,7 +740,9 @@ static int tile_cols(int M)
         const char *env = getenv("WRP_TILE_COLS");
         t = env && atoi(env) == 4 ? 4 : 8; // 8 columns (64-byte row segments) measured 24 % faster than 4
     }
-    return M == 4096 ? 4 : t; // 4096 rows: 4 columns fill the 128 KiB tile of the 16-warp CTA
+    // 4096 rows: 4 columns = 128 KiB tiles, one 16-warp CTA per SM.  (2 columns = 64 KiB tiles with two
+    // 8-warp CTAs per SM was measured 20 % slower: 16-byte row pieces, 10x the bank conflicts.)
+    return M == 4096 ? 4 : t;
 }
 
 cudaError_t persistent_setup()
@@ -787,7 +801,8 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.b3_first = S > L ? S - L : 0;
     p.total_items = S * (p.tiles_a + p.blocks_b);
     p.smax = smax;
-    p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : 1;
+    // (M = 4096: the hand-off of even one sector exceeds L2, so protecting it buys nothing; measured 5 % slower)
+    p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : (M == 1024);
     p.discard = getenv("WRP_DISCARD") ? atoi(getenv("WRP_DISCARD")) : 0; // -2 % throughput; evict-first already keeps the ring in L2
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     p.range_res = range_res;
