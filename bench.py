@@ -299,6 +299,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     wire_resident = S2 * steps / (w0.elapsed_time(w1) * 1e-3)
     clocks = sampler.stop()
+    del d_wire, d_out2
+
+    # ---- side figure: the stress shape (BASELINE config 5: M = 4096, N = 1024, 64 sectors resident per GPU) ----
+    stress = None
+    if args.stress_sectors > 0:
+        SM_, SN_, SS_ = 4096, 1024, args.stress_sectors
+        sx = synth.to_planar(synth.make_sector_int16(SM_, SN_, 0, 0), C)
+        d_sx = torch.from_numpy(np.ascontiguousarray(sx).view(np.float32).reshape(-1)).to(dev).repeat(SS_)
+        d_so = torch.empty((SS_, SM_ // 2, 2), dtype=torch.float32, device=dev)
+        with wrp.RadarChain(local_rank, n_rows_M=SM_, n_cols_N=SN_, n_channels=C, max_batch=1) as sch:
+            for _ in range(2):
+                sch.process_device(d_sx.data_ptr(), SS_, d_so.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(5):
+                sch.process_device(d_sx.data_ptr(), SS_, d_so.data_ptr(), stream.cuda_stream)
+            s1.record(stream)
+            torch.cuda.synchronize()
+        sv = SS_ * 5 / (s0.elapsed_time(s1) * 1e-3)
+        sbytes = C * SM_ * SN_ * 8 + (SM_ // 2) * 2 * 4
+        stress = {"value": sv, "unit": "sectors/s per GPU", "shape": f"{SM_}x{SN_}x{C} c64", "sectors_resident": SS_,
+                  "algorithmic_bytes_per_sector": sbytes, "gbs": sv * sbytes / 1e9}
+        del d_sx, d_so
 
     # cross-check: the wire path and the planar path see the same sectors -> same products
     n_chk = min(S, S2, 4)
@@ -339,6 +363,7 @@ def run_ours(args):
                               "hbm_frac": wire_resident * ALGO_BYTES_WIRE / 1e9 / peak,
                               "note": "HBM-resident int16 wire sectors: decode pre-pass + chain kernel per chunk of up to 64 sectors"},
             "chain_hbm_frac": chain_gbs / peak,
+            "stress_4096x1024": None if stress is None else dict(stress, hbm_frac=stress["gbs"] / peak),
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": sectors_per_launch * ALGO_BYTES_C64,
@@ -366,6 +391,8 @@ def main():
     ap.add_argument("--e2e-sectors", type=int, default=143, help="sectors per GPU per step (host leg)")
     ap.add_argument("--host-piece", type=int, default=8, help="sectors per pinned-ring piece")
     ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--stress-sectors", type=int, default=64,
+                    help="sectors of the 4096x1024 stress shape kept resident for the side figure (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="non-zero: shorten the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "ours":

@@ -62,8 +62,9 @@ typedef enum {
     /* one persistent kernel per batch: range-FFT tiles (window on load) and Doppler blocks
      * (mean removal, shift/clip, |.|^2, moving-average power, dB products in the epilogue)
      * interleaved on every SM; the hand-off between them lives in an L2-resident ring,
-     * every other intermediate in registers/shared memory.  (WRP_FUSED_IMPL=v1 in the
-     * environment selects the earlier two-kernel form.) */
+     * every other intermediate in registers/shared memory.  Built for M = 1024 or 4096
+     * with N = 512 or 1024 (other shapes: WRP_ERR_UNSUPPORTED, use WRP_MODE_STAGED).
+     * (WRP_FUSED_IMPL=v1 in the environment selects the earlier two-kernel form, M = 1024.) */
     WRP_MODE_FUSED = 0,
     /* the reference's kernel cascade stage by stage (rpv2.cu:409-570), every stage
      * materialised in device memory so wrp_dump_stage can return 00iq..10zdr. */
