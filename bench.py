@@ -381,6 +381,73 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_volume(args):
+    """BASELINE config 4: one volume scan = 9 elevations x 143 sectors = 1287 wire-format
+    sectors in pinned host memory, sharded contiguously over the ranks, product volume gathered.
+    Strong scaling; one step = one volume.  Not the default bench line (that is config 2/3)."""
+    import torch
+    import torch.distributed as dist
+
+    wrp = importlib.import_module("weather-radar-processing_b200")
+    synth = wrp.synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, E = 143, 9
+    U = S * E
+    lo, hi = wrp.volume.shard_bounds(U, rank, world)
+    base = [synth.to_wire(synth.make_sector_int16(M, N, s, 0)) for s in range(8)]
+    pin = wrp.PinnedBuffer((hi - lo) * M * N * 12)
+    view = pin.array.reshape(hi - lo, M * N * 12)
+    for k in range(lo, hi):
+        view[k - lo] = base[k % 8].reshape(-1)
+    chain = wrp.RadarChain(local_rank, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=args.host_piece, n_streams=args.streams)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        vol = wrp.volume.process_volume(chain, pin, U, dev)
+    barrier()
+    l0 = chain.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vol = wrp.volume.process_volume(chain, pin, U, dev)
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    v = vol.cpu().numpy()
+    ok = v.shape == (U, M // 2, 2) and np.isfinite(v[:, 1:]).all() and all(
+        np.array_equal(v[k], v[k % 8]) for k in range(0, U, 97))
+    if not ok:
+        raise SystemExit("bench.py: gathered volume is wrong")
+    if rank == 0:
+        value = U * args.steps / dt
+        print(json.dumps({
+            "metric": "sectors_per_s", "value": value, "unit": "sectors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "volume scan 9 elevations x 143 sectors, wire int16 from pinned host memory, "
+                                   "contiguous (elevation, sector) shards, product volume all-gathered",
+                       "M": M, "N": N, "channels": C, "units": U},
+            "e2e": {"value": value, "unit": "sectors/s", "h2d_bytes_per_step": U * M * N * 12,
+                    "d2h_bytes_per_step": U * M * 4, "h2d_gbs_per_gpu": value / world * M * N * 12 / 1e9},
+            "volume_bytes": int(v.nbytes), "gpu_launches": int(chain.launch_count - l0)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,12 +460,16 @@ def main():
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--stress-sectors", type=int, default=64,
                     help="sectors of the 4096x1024 stress shape kept resident for the side figure (0 = skip)")
+    ap.add_argument("--workload", default="sector", choices=["sector", "volume"],
+                    help="sector: the default line (configs 2/3); volume: config 4, one 9 x 143 volume scan, strong scaling")
     ap.add_argument("--cpu-sample", type=int, default=0, help="non-zero: shorten the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "volume":
+        run_volume(args)
     else:
         run_ours(args)
 

@@ -413,3 +413,22 @@ def test_large_batch_is_deterministic_and_order_independent(wrp, sectors, refs):
     for i in range(n):
         assert np.array_equal(a[i], single[(i * 7) % 3]), f"sector {i}"
         assert_products_close(a[i], refs[(i * 7) % 3].zdb, refs[(i * 7) % 3].zdr, f"sector {i}")
+
+
+def test_volume_scan_single_rank(wrp, sectors, refs):
+    """Config 4 driver on one rank: 2 elevations x 5 sectors of wire input through process_volume;
+    the volume comes back in (elevation, sector) order and every unit matches the oracle."""
+    torch = pytest.importorskip("torch")
+    S, E = 5, 2
+    wire = np.stack([wrp.synth.to_wire(sectors[(k * 2) % 3]) for k in range(S * E)])
+    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=4) as ch:
+        vol = wrp.volume.process_volume(ch, wire, S * E, torch.device("cuda", 0)).cpu().numpy()
+    assert vol.shape == (S * E, M // 2, 2)
+    for k in range(S * E):
+        r = refs[(k * 2) % 3]
+        assert_products_close(vol[k], r.zdb, r.zdr, f"unit {k}")
+    flat = wrp.volume.as_sitdim(vol, S, E)
+    s, e = wrp.volume.unit_to_ids(7, S)
+    assert (s, e) == (2, 1)
+    off = wrp.Dimension4(2, M // 2, S, E).copy_at_depth(0, 0, s, e)
+    assert np.array_equal(flat[off:off + M], vol[7].reshape(-1))

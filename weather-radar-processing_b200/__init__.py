@@ -17,7 +17,7 @@ import subprocess
 
 import numpy as np
 
-from . import dumpio, synth  # noqa: F401  (re-exported helpers)
+from . import dumpio, synth, volume  # noqa: F401  (re-exported helpers)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)

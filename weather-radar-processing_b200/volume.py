@@ -51,6 +51,32 @@ def gather_volume(local, n_units: int, group=None):
     return torch.cat(parts, dim=0)
 
 
+def process_shard(chain, shard_input, n_local: int, out=None):
+    """Run a rank's contiguous block of units (already in ``chain``'s input format, host memory)
+    through ``wrp_process_host``; returns float32 ``[n_local, gates, 2]``."""
+    if out is None:
+        out = np.empty((n_local, chain.M // 2, 2), np.float32)
+    if n_local:
+        chain.process_host(shard_input, n_local, out)
+    return out
+
+
+def process_volume(chain, shard_input, n_units: int, device, group=None):
+    """One volume scan on this rank's shard + the gather: returns the ``[n_units, gates, 2]`` product
+    volume as a torch tensor on ``device`` (every rank gets it).  ``shard_input`` holds the units
+    ``shard_bounds(n_units, rank, world)`` of this rank."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    lo, hi = shard_bounds(n_units, rank, world)
+    local = torch.from_numpy(process_shard(chain, shard_input, hi - lo)).to(device)
+    return local if world == 1 else gather_volume(local, n_units, group)
+
+
 def as_sitdim(volume: np.ndarray, n_sectors: int, n_elevations: int) -> np.ndarray:
     """[E*S, gates, 2] -> the reference's flat ``result`` array (sitdim order, rpv2.cu:736)."""
     v = np.asarray(volume)
