@@ -207,6 +207,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = wrp.bind_host_to_gpu(local_rank) if world > 1 and not os.environ.get("WRP_NO_BIND") else []
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S = args.sectors
@@ -371,7 +372,8 @@ def run_ours(args):
                          "kernel_share_of_step": ms_k / ms},
             "e2e": {"value": e2e_value, "unit": "sectors/s", "h2d_bytes_per_step": S2 * M * N * 12,
                     "d2h_bytes_per_step": S2 * M * 4, "input_fmt": "wire_i16be", "sectors_per_step_per_gpu": S2,
-                    "h2d_gbs": e2e_value / world * M * N * 12 / 1e9, "api": "wrp_process_host"},
+                    "h2d_gbs": e2e_value / world * M * N * 12 / 1e9, "api": "wrp_process_host",
+                    "host_cores_bound_per_rank": len(numa_cores)},
             "gpu_launches": int(launches + launches_e2e),
             "clocks": clocks,
             "cpu_baseline": cpu,
@@ -397,6 +399,7 @@ def run_volume(args):
         raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = wrp.bind_host_to_gpu(local_rank) if world > 1 and not os.environ.get("WRP_NO_BIND") else []
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S, E = 143, 9
@@ -442,7 +445,8 @@ def run_volume(args):
                                    "contiguous (elevation, sector) shards, product volume all-gathered",
                        "M": M, "N": N, "channels": C, "units": U},
             "e2e": {"value": value, "unit": "sectors/s", "h2d_bytes_per_step": U * M * N * 12,
-                    "d2h_bytes_per_step": U * M * 4, "h2d_gbs_per_gpu": value / world * M * N * 12 / 1e9},
+                    "d2h_bytes_per_step": U * M * 4, "h2d_gbs_per_gpu": value / world * M * N * 12 / 1e9,
+                    "host_cores_bound_per_rank": len(numa_cores)},
             "volume_bytes": int(v.nbytes), "gpu_launches": int(chain.launch_count - l0)}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -136,6 +136,28 @@ def default_config(**overrides) -> Config:
     return cfg
 
 
+def bind_host_to_gpu(device: int) -> list[int]:
+    """Pin the calling process to the CPU cores NVML reports as local to ``device`` (same NUMA node /
+    PCIe root), so that pinned host buffers allocated afterwards are node-local and H2D copies do not
+    cross the socket interconnect.  Matters when several ranks stream from host memory at once (the
+    reference is single-GPU and never had to care).  Returns the cores chosen ([] = left unchanged)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = [c for c in cores if c in allowed]
+        if cores and len(cores) < len(allowed):
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:
+        pass
+    return []
+
+
 class PinnedBuffer:
     """Page-locked host memory (the reference's cudaMallocHost'ed p_iq, rpv2.cu:291)."""
 
