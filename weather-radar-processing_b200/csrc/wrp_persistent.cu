@@ -183,6 +183,7 @@ struct Item {
     int kind; // 0 = range tile, 1 = Doppler block, < 0 = queue empty
     int sector;
     int sub;
+    int slot; // x2 ring slot = sector % ring (a runtime division: done once, by the decoding thread)
 };
 
 // queue: n1 steps of [A]; n2 steps of [A, B]; n3 steps of [B]
@@ -194,6 +195,7 @@ __device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
         it.kind = 0;
         it.sector = idx / TA;
         it.sub = idx - it.sector * TA;
+        it.slot = it.sector % p.ring;
         return it;
     }
     idx -= p.n1 * TA;
@@ -209,6 +211,7 @@ __device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
             it.sector = t;
             it.sub = r - TA;
         }
+        it.slot = it.sector % p.ring;
         return it;
     }
     idx -= p.n2 * per;
@@ -216,6 +219,7 @@ __device__ __forceinline__ Item decode_item(int idx, const PersistParams &p)
     const int t = idx / TB;
     it.sector = p.b3_first + t;
     it.sub = idx - t * TB;
+    it.slot = it.sector % p.ring;
     return it;
 }
 
@@ -246,8 +250,7 @@ __device__ __forceinline__ const uint8_t *doppler_row(const Item &it, const Pers
         chn = p.C == 1 ? 0 : 2;
         gate = (it.sub - p.pair_blocks) * ROWS_B + warp * RPW + rr;
     }
-    const int slot = it.sector % p.ring;
-    return (const uint8_t *)p.x2 + (((size_t)slot * p.C + chn) * p.half_m + gate) * (size_t)(N * 8);
+    return (const uint8_t *)p.x2 + (((size_t)it.slot * p.C + chn) * p.half_m + gate) * (size_t)(N * 8);
 }
 // The ring rows are scratch: once a Doppler block has them in shared memory their L2 lines are
 // dropped, so the dirty lines are never written back to DRAM
@@ -351,19 +354,19 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
         mbar_init(&mbar, THREADS);
         const int first = atomicAdd(p.ctrl, 1);
         claimed_next = atomicAdd(p.ctrl, 1);
-        Item f{-1, 0, 0};
+        Item f{-1, 0, 0, 0};
         if (first < p.total_items) {
             f = decode_item(first, p);
             int target;
             const int *dep = item_dep<T>(f, p, target);
             if (dep) spin_until(dep, target); // nothing is held yet: blocking is safe
         }
-        s_item[0] = make_int4(f.kind, f.sector, f.sub, 0);
+        s_item[0] = make_int4(f.kind, f.sector, f.sub, f.slot);
         s_seq = 1;
         s_go = 1;
     }
     __syncthreads();
-    Item it{s_item[0].x, s_item[0].y, s_item[0].z};
+    Item it{s_item[0].x, s_item[0].y, s_item[0].z, s_item[0].w};
     if (it.kind >= 0) issue_warp_load<N, T, Q>(it, p, tile, &mbar, warp, lane);
 
     uint32_t phase = 0;
@@ -392,13 +395,13 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
 
     while (it.kind >= 0) {
         const int nslot = (n + 1) & 1;
-        Item nit{-1, 0, 0};
+        Item nit{-1, 0, 0, 0};
         bool loaded = false;
         // Thread 0 works one item ahead: the queue slot of item n+1 was claimed during item n-1, so
         // it can be decoded and its dependency probed right now; the claim for item n+2 goes out at
         // the same time.  Both round trips hide behind this item's first pass; the results are
         // published (shared memory, no barrier) right after it.
-        Item cand{-1, 0, 0};
+        Item cand{-1, 0, 0, 0};
         int probe = 0, probe_target = 0, claimed_next2 = 0;
         const int *probe_dep = nullptr;
         if (tid == 0) {
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 bool ready = probe >= probe_target;
                 if (!ready) ready = ld_relaxed(probe_dep) >= probe_target; // the early probe may be stale
                 if ((p.debug & 16) && cand.kind >= 0 && !ready) atomicAdd(p.ctrl + 1 + cand.kind, 1);
-                s_item[nslot] = make_int4(cand.kind, cand.sector, cand.sub, 0);
+                s_item[nslot] = make_int4(cand.kind, cand.sector, cand.sub, cand.slot);
                 if (ready) s_go = n + 2; // before s_seq: whoever sees the item also sees that it may load
                 __threadfence_block();
                 s_seq = n + 2;
@@ -425,7 +428,10 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
         auto prefetch_next = [&]() {
             while (s_seq < n + 2) {
             }
-            nit = Item{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z};
+            {
+                const int4 pub = s_item[nslot];
+                nit = Item{pub.x, pub.y, pub.z, pub.w};
+            }
             if (nit.kind >= 0 && s_go >= n + 2) {
                 issue_warp_load<N, T, Q>(nit, p, tile, &mbar, warp, lane);
                 loaded = true;
@@ -554,10 +560,13 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             }
             const int ka = b; // rows 32 ka + .. of warp w (ka = 32/T * w ..) are its own 8 KiB region
             {
-                const uint32_t off_sw = (uint32_t)(ka * (R * PITCH) + c * 8) | (uint32_t)((ka & SW) * PITCH);
+                // row 32 ka + (bb ^ (ka & SW)): SW + 1 swizzled bases, everything else is an immediate
+                const uint8_t *s_sw[SW + 1];
+#pragma unroll
+                for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = stile + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
                 static_for<R>([&](auto bi) {
                     constexpr int bb = decltype(bi)::value;
-                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(stile + (off_sw ^ (uint32_t)(bb * PITCH)));
+                    v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(s_sw[bb & SW] + (bb & ~SW) * PITCH);
                 });
             }
             __syncwarp();
@@ -566,7 +575,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             {
                 // sub-transform output k' = ka + 32 kb < 512 is row Q k' + sub of the M-point transform
                 float2 *out =
-                    p.x2 + (((size_t)(it.sector % p.ring) * p.C + ch) * p.half_m + Q * ka + sub) * (size_t)N + col;
+                    p.x2 + (((size_t)it.slot * p.C + ch) * p.half_m + Q * ka + sub) * (size_t)N + col;
                 static_for<R / 2>([&](auto ki) { // rows k < M/2
                     constexpr int kb = decltype(ki)::value;
                     out[(size_t)(Q * R * kb) * N] = v[kb];
@@ -655,10 +664,12 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             const int ka = RPW == 2 ? (lane & 15) : lane;
             {
                 const uint8_t *grp = region + rsel * (N * 8) + ka * 256;
-                const int sw = (ka & 7) * 16;
+                const uint8_t *g_sw[8]; // 16-byte chunk cc of group ka sits at chunk cc ^ (ka & 7)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g_sw[k] = grp + ((k ^ (ka & 7)) * 16);
                 static_for<16>([&](auto ci) {
                     constexpr int cc = decltype(ci)::value;
-                    const float4 q = *reinterpret_cast<const float4 *>(grp + ((cc * 16) ^ sw));
+                    const float4 q = *reinterpret_cast<const float4 *>(g_sw[cc & 7] + (cc & 8) * 16);
                     u[brev<32>(2 * cc)] = make_float2(q.x, q.y);
                     u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
                 });
