@@ -373,21 +373,31 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
     int n = 0;        // index of the current item in this CTA's sequence
     int pending = -1;   // sector of a finished range tile whose completion this CTA has not published yet
     int pending_b = -1; // sector of a Doppler block whose ring rows were consumed (and discarded) but not yet reported
-    // One release per item per CTA without a blocking CTA barrier: every warp but warp 0 only
-    // announces (bar.arrive) that it is past the stores / discards in question; warp 0 waits for
-    // the announcements (bar.sync) and its lane 0 publishes.  Both variables are CTA-uniform (all
-    // warps walk the same item sequence).
+    // One release per item per CTA without a blocking CTA barrier: every warp but the last only
+    // announces (bar.arrive) that it is past the stores / discards in question; the last warp waits
+    // for the announcements (bar.sync) and its lane 0 publishes (warp 0 carries the queue work and
+    // must not be held up).  Both variables are CTA-uniform (all warps walk the same item sequence).
+    auto release_pending = [&]() {
+        if (pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
+        if (pending_b >= 0) red_release_add(p.ctrl + CTRL_A + p.smax + pending_b);
+    };
     auto publish_pending = [&]() {
         if (pending >= 0 || pending_b >= 0) {
-            if (warp == 0) {
+            if (warp == NW - 1) {
                 bar_sync(1, THREADS);
-                if (lane == 0) {
-                    if (pending >= 0) red_release_add(p.ctrl + CTRL_A + pending);
-                    if (pending_b >= 0) red_release_add(p.ctrl + CTRL_A + p.smax + pending_b);
-                }
+                if (lane == 0) release_pending();
             } else {
                 bar_arrive(1, THREADS);
             }
+            pending = -1;
+            pending_b = -1;
+        }
+    };
+    // Same publication right after a CTA-wide barrier of the current item: the barrier already is
+    // the rendezvous (every warp's stores of the previous item precede it), so nobody waits
+    auto publish_pending_after_cta_barrier = [&]() {
+        if (pending >= 0 || pending_b >= 0) {
+            if (tid == THREADS - 32) release_pending();
             pending = -1;
             pending_b = -1;
         }
@@ -491,6 +501,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                         *reinterpret_cast<float4 *>(ptr + q * (1024 * PITCH)) = make_float4(e[q].x, e[q].y, o[q].x, o[q].y);
                 }
                 __syncthreads();
+                publish_pending_after_cta_barrier();
             }
             float2 v[R];
             {
@@ -525,8 +536,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             } else {
                 fft_dit<R, -1>(v);
             }
-            publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
-            publish_pending();
+            publish_next();
             __syncwarp();
             {
                 // Z[ka][b] goes to row 32 ka + (b ^ (ka & SW)): the warp keeps its own row footprint
@@ -551,8 +561,10 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             }
             // the exchange: the one barrier of a 1024-point column group (the whole CTA for Q = 1, the
             // 32 T threads of a sub-tile for Q = 4)
-            if constexpr (Q == 1) __syncthreads();
-            else { // constant barrier ids, so that only 6 of the 16 are reserved
+            if constexpr (Q == 1) {
+                __syncthreads();
+                publish_pending_after_cta_barrier();
+            } else { // constant barrier ids, so that only 6 of the 16 are reserved
                 if (sub == 0) bar_sync_id<2>(32 * T);
                 else if (sub == 1) bar_sync_id<3>(32 * T);
                 else if (sub == 2) bar_sync_id<4>(32 * T);
@@ -656,7 +668,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                     }
                 }
             }
-            publish_next();    // first: warp 0 may wait inside publish_pending for the other warps
+            publish_next();
             publish_pending();
             __syncwarp();
             float2 u[32];
