@@ -131,6 +131,42 @@ def test_fused_equals_staged(wrp, sectors):
     assert np.max(np.abs(a[:, 1:] - b[:, 1:])) <= 1e-3
 
 
+@pytest.mark.parametrize("n", [512, 1024])
+def test_doppler_energy_form_equals_fft_form(wrp, oracle, monkeypatch, n):
+    """The default Doppler block evaluates stages 03-08 by Parseval (row energy minus the DC bin and
+    the two clipped bins); WRP_DOPPLER=fft runs the literal two-pass transform, shift, clip, |.|^2.
+    Both must give the oracle's products, and agree with each other far inside the 0.01 dB budget."""
+    secs = [wrp.synth.to_planar(wrp.synth.make_sector_int16(M, n, s, 0)) for s in range(2)]
+    refs_n = [oracle.chain(x.astype(np.complex128)) for x in secs]
+    data = np.stack(secs * 5)  # 10 sectors: more than the x2 ring holds
+    outs = {}
+    for form in ("energy", "fft"):
+        monkeypatch.setenv("WRP_DOPPLER", form)
+        with wrp.RadarChain(0, n_cols_N=n) as ch:
+            outs[form] = ch.process_host(data, len(data))
+    monkeypatch.delenv("WRP_DOPPLER")
+    for form, out in outs.items():
+        for i in range(len(data)):
+            assert_products_close(out[i], refs_n[i % 2].zdb, refs_n[i % 2].zdr, f"{form} N={n} sector {i}")
+    assert np.max(np.abs(outs["energy"][:, 1:] - outs["fft"][:, 1:])) <= 1e-4
+    assert not np.array_equal(outs["energy"], outs["fft"])  # the switch really selects two code paths
+
+
+def test_doppler_energy_form_near_nyquist_target(wrp, oracle):
+    """Worst case for the energy form: a target whose Doppler line sits ON the clipped bins, so
+    most of the row energy is subtracted again.  The Doppler window leaves the skirts of the line
+    outside the clipped bins, and the products still match the oracle within 0.01 dB."""
+    i, j = np.arange(M)[:, None], np.arange(N)[None, :]
+    rng = np.random.default_rng(5)
+    tone = 4000.0 * np.exp(2j * np.pi * (0.2 * i + (1.5 / N - 0.5) * j))
+    noise = rng.normal(0, 30, (3, M, N)) + 1j * rng.normal(0, 30, (3, M, N))
+    x = (np.stack([tone, 0.6 * tone, 0.05 * tone]) + noise).astype(np.complex64)
+    ref = oracle.chain(x.astype(np.complex128))
+    with wrp.RadarChain(0) as ch:
+        out = ch.process_host(x[None], 1)[0]
+    assert_products_close(out, ref.zdb, ref.zdr, "near-Nyquist line")
+
+
 @pytest.mark.parametrize("channels", [1, 2])
 def test_fewer_channels(wrp, oracle, sectors, channels):
     data = np.stack([wrp.synth.to_planar(x, channels) for x in sectors[:2]])

@@ -177,3 +177,43 @@ def test_error_metric_and_float_codec(oracle):
         assert b == np.array([v], ">f4").tobytes()
         back = oracle.btof(b)
         assert back == np.float32(v) or (np.isinf(v) and np.isinf(back))
+
+
+def test_energy_form_of_the_doppler_stage_on_oracle_spectra(oracle, wrp):
+    """The identity the fused kernel's Doppler block uses (Parseval): with Y the un-normalised
+    Doppler transform of a range-FFT row x,  sum_{b != 0, N/2-1, N/2-2} |Y_b|^2 =
+    N sum_j |x_j|^2 - |Y_0|^2 - |Y_{N/2-1}|^2 - |Y_{N/2-2}|^2, because the mean removal zeroes bin 0
+    (read.cc:193-201) and the clip zeroes shifted columns N-1, N-2 (read.cc:222-224).  Checked on
+    the oracle's own stage-02 rows against its stage-08 row power, in float32 arithmetic ordered
+    like the kernel (16 strided partials per lane, then a tree over 32 lanes)."""
+    M, N = 1024, 512
+    x = wrp.synth.to_planar(wrp.synth.make_sector_int16(M, N, 2, 1))
+    ref = oracle.chain(x.astype(np.complex128), dumps=True)
+    x2 = ref.stages["s02_fft1"][:, :M // 2, :].astype(np.complex64)
+
+    def lane_tree_sum(a):
+        part = a.reshape(a.shape[:-1] + (N // 32, 32))
+        acc = part[..., 0, :]
+        for k in range(1, N // 32):
+            acc = (acc + part[..., k, :]).astype(a.dtype)
+        w = 16
+        while w:
+            acc = (acc[..., :w] + acc[..., w:2 * w]).astype(a.dtype)
+            w //= 2
+        return acc[..., 0]
+
+    def abs2(z):
+        return (z.real.astype(np.float32) ** 2 + z.imag.astype(np.float32) ** 2).astype(np.float32)
+
+    j = np.arange(N)
+    energy = lane_tree_sum(abs2(x2))
+    removed = abs2(lane_tree_sum(x2))
+    for m in (1, 2):
+        tw = np.exp(2j * np.pi * j * (N // 2 - m) / N).astype(np.complex64)
+        removed = removed + abs2(lane_tree_sum((x2 * tw).astype(np.complex64)))
+    power = (np.float32(N) * energy - removed).astype(np.float64)
+    want = np.asarray(ref.stages["power"], np.float64)[:, :M // 2]
+    assert np.max(np.abs(power / want - 1)) < 5e-6  # 2e-5 dB
+    # the subtraction never cancels more than ~3/4 of the row energy: the Doppler window spreads
+    # any line over three bins, only bin 0 and two edge bins are removed
+    assert np.max(removed / (np.float32(N) * energy)) < 0.9

@@ -29,6 +29,7 @@
 // (ld.relaxed.gpu probe; data is then read with cp.async.cg straight from L2).  An item only waits
 // for items earlier in the queue, and nobody spins while holding unpublished work: no deadlock.
 #include <cstdlib>
+#include <cstring>
 
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
@@ -79,11 +80,18 @@ __device__ __forceinline__ uint64_t policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ void cp_async16_evict_first(void *dst, const void *src, uint64_t pol)
+__device__ __forceinline__ void cp_async16_evict_first(uint32_t dst_smem, const void *src, uint64_t pol)
 {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
-                 "l"(pol)
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol)
                  : "memory");
+}
+// A shared-memory address ptxas cannot split into register + uniform base (XOR with a kernel
+// parameter that is always 0): the hinted LDGSTS has no room for a uniform address offset next to
+// its uniform policy operand, and ptxas 12.9 overwrites the low policy word with the offset and
+// emits a "[R+UR], desc[URodd]" encoding that traps (tools/check_sass.py guards the build).
+__device__ __forceinline__ uint32_t opaque_smem_addr(const void *p, int zero)
+{
+    return smem_u32(p) ^ (uint32_t)zero;
 }
 // arrive on `bar` once every cp.async this thread has issued so far has landed
 __device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
@@ -151,6 +159,7 @@ struct PersistParams {
     int evict_first; // stream the input through L2 with an evict-first policy (WRP_EVICT_FIRST=0 turns it off)
     int discard; // drop consumed ring rows from L2 with discard.global.L2 (WRP_DISCARD=1 turns it on)
     int debug; // WRP_DEBUG development switches
+    int zero;  // always 0 (see opaque_smem_addr)
     float range_res, calib, taps_sum;
 };
 constexpr int CTRL_A = 32;
@@ -176,7 +185,9 @@ template <int R1B, int T, int Q> struct Tables {
     static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + TAB_WRC : OFF_TW4 + 1024 * 8;
     static constexpr int OFF_TWB = OFF_TWA + TAB_TWA;
     static constexpr int OFF_WD = OFF_TWB + TWB;
-    static constexpr int SMEM = OFF_WD + WD;
+    // energy form of the Doppler stage: per-lane factors of the two clipped bins, [32] float4
+    static constexpr int OFF_TL = OFF_WD + WD;
+    static constexpr int SMEM = OFF_TL + 32 * 16;
 };
 
 struct Item {
@@ -277,9 +288,10 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
         // register for the hinted form — see cp_async16_evict_first)
         if (p.evict_first) {
             const uint64_t pol = policy_evict_first();
+            const uint32_t d = opaque_smem_addr(dst, p.zero);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                cp_async16_evict_first(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8), pol);
+                cp_async16_evict_first(d + k * 512, src + (size_t)k * (32 / CPR) * (N * 8), pol);
         } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / CPR) * (N * 8));
@@ -302,7 +314,7 @@ __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistPar
 // Q = 4: a radix-4 decimation-in-frequency pre-pass (window folded in) turns the T columns x 4096
 // rows into 4T independent 1024-point columns, one per warp, whose outputs k' < 512 are the rows
 // 4 k' + k0 < M/2 of the 4096-point transform — so the pruning and both 32 x 32 passes are shared.
-template <int R1B, int T, int Q>
+template <int R1B, int T, int Q, int DOP>
 __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
     chain_persistent_kernel(const PersistParams p)
 {
@@ -348,6 +360,14 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
         copy_rows(Tab::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
         copy_rows(Tab::OFF_TWB, p.tw_b, 32, R1B * 8, Tab::TWB_ROW);
         copy_rows(Tab::OFF_WD, p.wd, 1, Tab::WD, Tab::WD);
+        if (DOP == 1 && tid < 32) {
+            // t_m(l) = (-1)^l exp(-2 pi i l m / N), m = 1, 2: lane l's factor of clipped bin N/2 - m
+            float s1, c1, s2, c2;
+            sincospif(-2.f * (float)tid / (float)N, &s1, &c1);
+            sincospif(-4.f * (float)tid / (float)N, &s2, &c2);
+            const float sg = (tid & 1) ? -1.f : 1.f;
+            *reinterpret_cast<float4 *>(tile + Tab::OFF_TL + tid * 16) = make_float4(sg * c1, sg * s1, sg * c2, sg * s2);
+        }
     }
     int claimed_next = 0; // thread 0: queue index of the item after the current one (claimed one item ahead)
     if (tid == 0) {
@@ -614,93 +634,172 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
             }
             const bool pair = it.sub < p.pair_blocks;
             uint8_t *region = tile + warp * 8192; // rows (warp, rr) live at region + rr * N*8
-            {
-                const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWB + lane * Tab::TWB_ROW);
-                // two rows per warp: the inter-pass twiddles stay in registers across both rows;
-                // one row (N = 1024): they are read as they are used, two steps ahead of the stores
-                float2 tw[RPW == 2 ? R1B : 2];
-                if constexpr (RPW == 2) {
-                    static_for<R1B / 2>([&](auto qi) {
-                        constexpr int q = decltype(qi)::value;
-                        const float4 w = t4[q];
-                        tw[2 * q] = make_float2(w.x, w.y);
-                        tw[2 * q + 1] = make_float2(w.z, w.w);
-                    });
-                }
-#pragma unroll 1
-                for (int rr = 0; rr < RPW; ++rr) {
-                    uint8_t *row = region + rr * (N * 8);
+            const int rsel = RPW == 2 ? (lane >> 4) : 0; // which of the warp's rows this lane reports
+            const int ka = RPW == 2 ? (lane & 15) : lane;
+            float pw;
+            if constexpr (DOP == 1) {
+                // ---- energy form of stages 03-08 (Parseval) ----
+                // The row power is the sum of |Y_b|^2 over every Doppler bin b except the DC bin (zeroed
+                // by the mean removal, rpv2.cu:93-130) and the two clipped bins N/2-1, N/2-2 (columns
+                // N-1, N-2 after the shift, rpv2.cu:137-148).  With Y the un-normalised transform,
+                //   sum_b |Y_b|^2 = N sum_j |x_j|^2,   so   P = N E - |Y_0|^2 - |Y_{N/2-1}|^2 - |Y_{N/2-2}|^2:
+                // one pass over the row, three DFT bins instead of N.  Lane l holds x[32 a + l]; bin
+                // N/2 - m is sum_l (-1)^l e^{-2 pi i l m / N} D_m(l) with D_m(l) bin m of the forward
+                // R1B-point DFT over a.  The Doppler window spreads every line over three bins, so
+                // some of a row's energy always lies outside the removed bins: >= 27 % on the synthetic
+                // sectors (5e-7 relative against the double oracle), 2 % for a line placed exactly between
+                // the two clipped bins (3e-5 dB, tests/test_gpu_parity.py).
+                const float4 tl = *reinterpret_cast<const float4 *>(tile + Tab::OFF_TL + lane * 16);
+                float q[RPW][7];
+                static_for<RPW>([&](auto ri) {
+                    constexpr int rr = decltype(ri)::value;
+                    const uint8_t *row = region + rr * (N * 8);
                     float2 v[R1B];
                     static_for<R1B>([&](auto ai) {
                         constexpr int a = decltype(ai)::value;
-                        v[brev<R1B>(a)] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
+                        v[a] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
                     });
-                    fft_dit<R1B, +1>(v);
-                    // mean removal (rpv2.cu:93-130): only the a-sum (ka = 0) carries the row mean
-                    float sx = v[0].x, sy = v[0].y;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+#ifndef WRP_PV_LATE
+                    if constexpr (rr == RPW - 1) { // the warp's region is in registers: fetch the next item
+                        publish_next();
+                        publish_pending();
+                        __syncwarp();
+                        prefetch_next();
                     }
-                    v[0].x -= sx * (1.f / 32.f);
-                    v[0].y -= sy * (1.f / 32.f);
-                    __syncwarp();
-                    // Z_l[ka] -> float2 index 32 ka + (l ^ ((ka & 7) << 1)): 16-byte chunks of group ka
-                    // are XOR-swizzled so pass 2's 128-bit reads are conflict-free
+#endif
+                    float2 e2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                    static_for<R1B>([&](auto ai) { // (sum re^2, sum im^2), one FFMA2 per sample
+                        constexpr int a = decltype(ai)::value;
+                        e2[a & 1] = cfma2(v[a], v[a], e2[a & 1]);
+                    });
+                    const float2 es = cadd(e2[0], e2[1]);
+                    float2 b0, b1, b2;
+                    dft_bins012<R1B>(v, b0, b1, b2);
+                    const float2 y1 = cmul(b1, make_float2(tl.x, tl.y)), y2 = cmul(b2, make_float2(tl.z, tl.w));
+                    q[rr][0] = es.x + es.y;
+                    q[rr][1] = b0.x;
+                    q[rr][2] = b0.y;
+                    q[rr][3] = y1.x;
+                    q[rr][4] = y1.y;
+                    q[rr][5] = y2.x;
+                    q[rr][6] = y2.y;
+                });
+#ifdef WRP_PV_LATE
+                publish_next();
+                publish_pending();
+                __syncwarp();
+                prefetch_next();
+#endif
+                // lane sums: with two rows per warp the first exchange also transposes, so the low
+                // half-warp ends up with row 0 (hh) and the high one with row 1 (vv)
+                float r[7];
+                if constexpr (RPW == 2) {
+                    const bool hi = lane >= 16;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float send = hi ? q[0][k] : q[RPW - 1][k], keep = hi ? q[RPW - 1][k] : q[0][k];
+                        r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) r[k] = q[0][k] + __shfl_xor_sync(0xffffffffu, q[0][k], 16);
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+                }
+                float removed = r[1] * r[1];
+#pragma unroll
+                for (int k = 2; k < 7; ++k) removed = fmaf(r[k], r[k], removed);
+                pw = fmaxf(fmaf((float)N, r[0], -removed), 0.f);
+            } else {
+                {
+                    const float4 *t4 = reinterpret_cast<const float4 *>(tile + Tab::OFF_TWB + lane * Tab::TWB_ROW);
+                    // two rows per warp: the inter-pass twiddles stay in registers across both rows;
+                    // one row (N = 1024): they are read as they are used, two steps ahead of the stores
+                    float2 tw[RPW == 2 ? R1B : 2];
                     if constexpr (RPW == 2) {
-                        static_for<R1B>([&](auto ki) {
-                            constexpr int ka = decltype(ki)::value;
-                            const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
-                            *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
-                        });
-                    } else {
-                        float4 wq[3] = {t4[0], t4[1], t4[2]};
                         static_for<R1B / 2>([&](auto qi) {
                             constexpr int q = decltype(qi)::value;
-                            const float4 w = wq[q % 3];
-                            if constexpr (q + 3 < R1B / 2) wq[q % 3] = t4[q + 3];
-                            const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
-                            const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
-                            *reinterpret_cast<float2 *>(row + (32 * (2 * q) + (lane ^ (((2 * q) & 7) << 1))) * 8) = y0;
-                            *reinterpret_cast<float2 *>(row + (32 * (2 * q + 1) + (lane ^ (((2 * q + 1) & 7) << 1))) * 8) = y1;
+                            const float4 w = t4[q];
+                            tw[2 * q] = make_float2(w.x, w.y);
+                            tw[2 * q + 1] = make_float2(w.z, w.w);
                         });
                     }
+#pragma unroll 1
+                    for (int rr = 0; rr < RPW; ++rr) {
+                        uint8_t *row = region + rr * (N * 8);
+                        float2 v[R1B];
+                        static_for<R1B>([&](auto ai) {
+                            constexpr int a = decltype(ai)::value;
+                            v[brev<R1B>(a)] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
+                        });
+                        fft_dit<R1B, +1>(v);
+                        // mean removal (rpv2.cu:93-130): only the a-sum (ka = 0) carries the row mean
+                        float sx = v[0].x, sy = v[0].y;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                        }
+                        v[0].x -= sx * (1.f / 32.f);
+                        v[0].y -= sy * (1.f / 32.f);
+                        __syncwarp();
+                        // Z_l[ka] -> float2 index 32 ka + (l ^ ((ka & 7) << 1)): 16-byte chunks of group ka
+                        // are XOR-swizzled so pass 2's 128-bit reads are conflict-free
+                        if constexpr (RPW == 2) {
+                            static_for<R1B>([&](auto ki) {
+                                constexpr int ka = decltype(ki)::value;
+                                const float2 y = ka == 0 ? v[0] : cmul(v[ka], tw[ka]);
+                                *reinterpret_cast<float2 *>(row + (32 * ka + (lane ^ ((ka & 7) << 1))) * 8) = y;
+                            });
+                        } else {
+                            float4 wq[3] = {t4[0], t4[1], t4[2]};
+                            static_for<R1B / 2>([&](auto qi) {
+                                constexpr int q = decltype(qi)::value;
+                                const float4 w = wq[q % 3];
+                                if constexpr (q + 3 < R1B / 2) wq[q % 3] = t4[q + 3];
+                                const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                                const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                                *reinterpret_cast<float2 *>(row + (32 * (2 * q) + (lane ^ (((2 * q) & 7) << 1))) * 8) = y0;
+                                *reinterpret_cast<float2 *>(row + (32 * (2 * q + 1) + (lane ^ (((2 * q + 1) & 7) << 1))) * 8) = y1;
+                            });
+                        }
+                    }
                 }
-            }
-            publish_next();
-            publish_pending();
-            __syncwarp();
-            float2 u[32];
-            const int rsel = RPW == 2 ? (lane >> 4) : 0;
-            const int ka = RPW == 2 ? (lane & 15) : lane;
-            {
-                const uint8_t *grp = region + rsel * (N * 8) + ka * 256;
-                const uint8_t *g_sw[8]; // 16-byte chunk cc of group ka sits at chunk cc ^ (ka & 7)
+                publish_next();
+                publish_pending();
+                __syncwarp();
+                float2 u[32];
+                {
+                    const uint8_t *grp = region + rsel * (N * 8) + ka * 256;
+                    const uint8_t *g_sw[8]; // 16-byte chunk cc of group ka sits at chunk cc ^ (ka & 7)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) g_sw[k] = grp + ((k ^ (ka & 7)) * 16);
-                static_for<16>([&](auto ci) {
-                    constexpr int cc = decltype(ci)::value;
-                    const float4 q = *reinterpret_cast<const float4 *>(g_sw[cc & 7] + (cc & 8) * 16);
-                    u[brev<32>(2 * cc)] = make_float2(q.x, q.y);
-                    u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
+                    for (int k = 0; k < 8; ++k) g_sw[k] = grp + ((k ^ (ka & 7)) * 16);
+                    static_for<16>([&](auto ci) {
+                        constexpr int cc = decltype(ci)::value;
+                        const float4 q = *reinterpret_cast<const float4 *>(g_sw[cc & 7] + (cc & 8) * 16);
+                        u[brev<32>(2 * cc)] = make_float2(q.x, q.y);
+                        u[brev<32>(2 * cc + 1)] = make_float2(q.z, q.w);
+                    });
+                }
+                __syncwarp();
+                prefetch_next();
+                fft_dit<32, +1>(u);
+                // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
+                // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
+                if (ka >= R1B - 2) u[15] = make_float2(0.f, 0.f); // the two clipped bins
+                float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                static_for<32>([&](auto ki) { // (sum re^2, sum im^2) with one FFMA2 per bin
+                    constexpr int kb = decltype(ki)::value;
+                    acc[kb & 3] = cfma2(u[kb], u[kb], acc[kb & 3]);
                 });
-            }
-            __syncwarp();
-            prefetch_next();
-            fft_dit<32, +1>(u);
-            // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
-            // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
-            if (ka >= R1B - 2) u[15] = make_float2(0.f, 0.f); // the two clipped bins
-            float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-            static_for<32>([&](auto ki) { // (sum re^2, sum im^2) with one FFMA2 per bin
-                constexpr int kb = decltype(ki)::value;
-                acc[kb & 3] = cfma2(u[kb], u[kb], acc[kb & 3]);
-            });
-            const float2 a2 = cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3]));
-            float pw = a2.x + a2.y;
+                const float2 a2 = cadd(cadd(acc[0], acc[1]), cadd(acc[2], acc[3]));
+                pw = a2.x + a2.y;
 #pragma unroll
-            for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+                for (int o = R1B / 2; o > 0; o >>= 1) pw += __shfl_xor_sync(0xffffffffu, pw, o);
+            }
             pw *= p.taps_sum; // stages 05-08: row sum of the circular convolution
             // (channel, gate) of this thread's row — the same map the loads use
             int chn, gate;
@@ -772,7 +871,10 @@ cudaError_t persistent_setup()
 {
     cudaError_t e;
 #define WRP_SET(R1B, T, Q)                                                                                   \
-    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T, Q, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             Tables<R1B, T, Q>::SMEM);                                                       \
+    if (e != cudaSuccess) return e;                                                                          \
+    e = cudaFuncSetAttribute(chain_persistent_kernel<R1B, T, Q, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              Tables<R1B, T, Q>::SMEM);                                                       \
     if (e != cudaSuccess) return e;
     WRP_SET(16, 8, 1)
@@ -828,6 +930,9 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : (M == 1024);
     p.discard = getenv("WRP_DISCARD") ? atoi(getenv("WRP_DISCARD")) : 0; // -2 % throughput; evict-first already keeps the ring in L2
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
+    // Doppler blocks: energy form (default) or the literal two-pass transform (WRP_DOPPLER=fft)
+    const char *dop = getenv("WRP_DOPPLER");
+    const bool doppler_fft = dop && !strcmp(dop, "fft");
     p.range_res = range_res;
     p.calib = calib;
     p.taps_sum = taps_sum;
@@ -860,7 +965,8 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
 #define WRP_LAUNCH(R1B, TT, QQ)                                                                              \
     do {                                                                                                     \
         cfg.dynamicSmemBytes = Tables<R1B, TT, QQ>::SMEM;                                                    \
-        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ>, p);                            \
+        if (doppler_fft) return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ, 0>, p);        \
+        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ, 1>, p);                         \
     } while (0)
     if (Q == 4) {
         if (N == 512) WRP_LAUNCH(16, 4, 4);
