@@ -9,7 +9,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --use_fast_math
 NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC
 LIB      := $(PKG)/libwrp.so
-OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
+OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_unified.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
 
 HOSTLIB  := $(PKG)/libwrphost.so
 HOSTSRC  := $(HOST)/dimension.cpp $(HOST)/sector.cpp $(HOST)/floats.c $(HOST)/radar_processor.cpp $(HOST)/stage_dump.cpp
@@ -28,7 +28,7 @@ $(HOST)/wrp_chain: $(HOST)/wrp_chain.cpp $(HOSTLIB)
 $(HOST)/host_selftest: $(HOST)/host_selftest.cpp $(HOSTLIB)
 	$(CXX) -O2 -std=c++17 -o $@ $< -L$(PKG) -lwrphost -lwrp -Wl,-rpath,'$$ORIGIN/..'
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/wrp_internal.h $(CSRC)/wrp_fft.cuh include/wrp.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/wrp_internal.h $(CSRC)/wrp_fft.cuh $(CSRC)/wrp_ptx.cuh $(CSRC)/wrp_chain_params.h include/wrp.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(CSRC)/wrp_tables.o: $(CSRC)/wrp_tables.cpp $(CSRC)/wrp_internal.h include/wrp.h

@@ -133,23 +133,28 @@ def test_fused_equals_staged(wrp, sectors):
 
 @pytest.mark.parametrize("n", [512, 1024])
 def test_doppler_energy_form_equals_fft_form(wrp, oracle, monkeypatch, n):
-    """The default Doppler block evaluates stages 03-08 by Parseval (row energy minus the DC bin and
+    """The default Doppler stage evaluates stages 03-08 by Parseval (row energy minus the DC bin and
     the two clipped bins); WRP_DOPPLER=fft runs the literal two-pass transform, shift, clip, |.|^2.
-    Both must give the oracle's products, and agree with each other far inside the 0.01 dB budget."""
+    For the default shape the energy form exists twice: in the unified-item kernel (default) and in
+    the two-kind work queue (WRP_CHAIN=queue).  All must give the oracle's products, and agree with
+    each other far inside the 0.01 dB budget."""
     secs = [wrp.synth.to_planar(wrp.synth.make_sector_int16(M, n, s, 0)) for s in range(2)]
     refs_n = [oracle.chain(x.astype(np.complex128)) for x in secs]
     data = np.stack(secs * 5)  # 10 sectors: more than the x2 ring holds
     outs = {}
-    for form in ("energy", "fft"):
-        monkeypatch.setenv("WRP_DOPPLER", form)
+    for form, env in (("default", {}), ("queue_energy", {"WRP_CHAIN": "queue"}), ("fft", {"WRP_DOPPLER": "fft"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with wrp.RadarChain(0, n_cols_N=n) as ch:
             outs[form] = ch.process_host(data, len(data))
-    monkeypatch.delenv("WRP_DOPPLER")
+        for k in env:
+            monkeypatch.delenv(k)
     for form, out in outs.items():
         for i in range(len(data)):
             assert_products_close(out[i], refs_n[i % 2].zdb, refs_n[i % 2].zdr, f"{form} N={n} sector {i}")
-    assert np.max(np.abs(outs["energy"][:, 1:] - outs["fft"][:, 1:])) <= 1e-4
-    assert not np.array_equal(outs["energy"], outs["fft"])  # the switch really selects two code paths
+    assert np.max(np.abs(outs["default"][:, 1:] - outs["fft"][:, 1:])) <= 1e-4
+    assert np.max(np.abs(outs["default"][:, 1:] - outs["queue_energy"][:, 1:])) <= 1e-4
+    assert not np.array_equal(outs["default"], outs["fft"])  # the switch really selects two code paths
 
 
 def test_doppler_energy_form_near_nyquist_target(wrp, oracle):

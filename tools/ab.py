@@ -68,6 +68,9 @@ def main():
         r = subprocess.run([sys.executable, __file__, "--child", "--sectors", str(args.sectors), "--reps", str(args.reps),
                             "--shape", args.shape, "--distinct", str(args.distinct), cfg], capture_output=True, text=True)
         sys.stdout.write(r.stdout if r.returncode == 0 else f"FAIL {cfg}: {r.stderr[-600:]}\n")
+        dbg = [l for l in r.stderr.splitlines() if l.startswith("[wrp debug]")]
+        if dbg:
+            sys.stdout.write("    " + dbg[-1] + "\n")
         sys.stdout.flush()
 
 

@@ -33,136 +33,11 @@
 
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
+#include "wrp_ptx.cuh"
+#include "wrp_chain_params.h"
 
 namespace wrp {
 
-// ---- PTX helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t"
-                 "}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// 16-byte async copy global -> shared (L1 bypass).  An L2 evict-first cache hint was tried here
-// (cp.async ... .L2::cache_hint): ptxas 12.9 allocated an odd uniform register for the LDGSTS
-// descriptor at one call site and the warp trapped with "illegal instruction"; st/ld
-// eviction-priority qualifiers need 256-bit vectors on sm_100.  WRP_L2_PERSIST pins the ring instead.
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-// Same copy with an L2 evict-first policy: the input is streamed once and should not push the x2
-// ring out of L2.  (With an earlier code shape ptxas 12.9 gave one call site an ODD uniform
-// descriptor register for this instruction form and the warp trapped with "illegal instruction";
-// tools/check_sass.py fails the build if that ever comes back.)
-__device__ __forceinline__ uint64_t policy_evict_first()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void cp_async16_evict_first(uint32_t dst_smem, const void *src, uint64_t pol)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol)
-                 : "memory");
-}
-// A shared-memory address ptxas cannot split into register + uniform base (XOR with a kernel
-// parameter that is always 0): the hinted LDGSTS has no room for a uniform address offset next to
-// its uniform policy operand, and ptxas 12.9 overwrites the low policy word with the offset and
-// emits a "[R+UR], desc[URodd]" encoding that traps (tools/check_sass.py guards the build).
-__device__ __forceinline__ uint32_t opaque_smem_addr(const void *p, int zero)
-{
-    return smem_u32(p) ^ (uint32_t)zero;
-}
-// arrive on `bar` once every cp.async this thread has issued so far has landed
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// producer/consumer named barrier: warps that only announce do not wait
-__device__ __forceinline__ void bar_arrive(int id, int threads)
-{
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void bar_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-template <int ID> __device__ __forceinline__ void bar_sync_id(int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(threads) : "memory");
-}
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// release-add: orders the executing thread's prior writes and, through the preceding __syncwarp,
-// its warp's (cumulativity); no L1 invalidation, unlike __threadfence()
-__device__ __forceinline__ void red_release_add(int *p)
-{
-    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-// probe without the L1 invalidate an acquire load carries: the counter is bumped by a release
-// (data is in L2 before the count moves) and everything read under it is fetched by cp.async.cg
-// straight from L2, issued after the value has been seen
-__device__ __forceinline__ int ld_relaxed(const int *p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void spin_until(const int *p, int target)
-{
-    while (ld_acquire(p) < target) __nanosleep(100);
-}
-
-// ---- parameters ----------------------------------------------------------------------------
-struct PersistParams {
-    const float *wrc_t;
-    const float *wd;
-    const float2 *tw_a;
-    const float2 *tw_b;
-    const float *wr4;   // M = 4096 only: wr(i)*c, natural order [4096]
-    const float2 *tw4;  // M = 4096 only: exp(-2*pi*i*r/4096), [1024]
-    const float2 *iq; // input [S][C][M][N]
-    float2 *x2;       // ring [ring][C][M/2][N]
-    float *out;       // [S][M/2][2]
-    float *power;     // optional [S][C][M/2]
-    int *ctrl;        // [0] work counter; [1..2] debug; a_done at CTRL_A; b_done at CTRL_A + smax
-    int S, C, N, half_m;
-    int ring, lag;
-    int tiles_a, blocks_b, pair_blocks;
-    int n1, n2, n3, b3_first; // queue regions (see decode_item)
-    int total_items;
-    int smax;
-    int evict_first; // stream the input through L2 with an evict-first policy (WRP_EVICT_FIRST=0 turns it off)
-    int discard; // drop consumed ring rows from L2 with discard.global.L2 (WRP_DISCARD=1 turns it on)
-    int debug; // WRP_DEBUG development switches
-    int zero;  // always 0 (see opaque_smem_addr)
-    float range_res, calib, taps_sum;
-};
-constexpr int CTRL_A = 32;
 // shared-memory copies of the small tables; rows are padded by 16 B so that the 128-bit reads of
 // lanes holding different rows hit different banks
 constexpr int WRC_ROW = 32 * 8 + 16; // wr(i)*c transposed [32][32], each value stored twice (w, w) for FMUL2
@@ -884,7 +759,7 @@ cudaError_t persistent_setup()
     WRP_SET(16, 4, 4)
     WRP_SET(32, 4, 4)
 #undef WRP_SET
-    return cudaSuccess;
+    return unified_setup();
 }
 
 // One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
@@ -939,6 +814,14 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
     if (e != cudaSuccess) return e;
+    // Default sector shape: the unified-item kernel (one item = range tile + eight Doppler rows,
+    // wrp_unified.cu).  WRP_CHAIN=queue keeps the two-kind work queue of this file.
+    {
+        const char *chain = getenv("WRP_CHAIN");
+        if (unified_supported(M, N) && T == 8 && !doppler_fft && !p.discard && l2_window_bytes == 0 &&
+            !(chain && !strcmp(chain, "queue")))
+            return launch_unified(p, sm_count, st);
+    }
     int grid = (16 / NW) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
 
