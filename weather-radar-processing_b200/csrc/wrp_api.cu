@@ -9,6 +9,7 @@
 // (rpv2.cu:422-491); scratch is owned by one compute stream so the reference's shared
 // d_tmp race cannot occur.
 #include "wrp_internal.h"
+#include "wrp_chain_params.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -159,6 +160,17 @@ static int create_impl(wrp_handle *h)
             if (M == 4096) { // 24-48 MiB of hand-off per sector: keep as few sectors in flight as the queue allows
                 h->x2_lag = 1;
                 h->x2_ring = 3;
+            }
+            {
+                // unified-item kernel (default shape, wrp_unified.cu): the rows of sector s are only one
+                // item per sector step behind its last tile, so the lag that keeps dependency waits rare
+                // is one sector larger than for the two-kind queue (measured: 4/8 251k, 5/10 270k, 6/12
+                // 265k sectors/s — 12 slots no longer fit L2 next to the input stream)
+                const char *chain = getenv("WRP_CHAIN"), *dop = getenv("WRP_DOPPLER");
+                if (wrp::unified_supported(M, N) && !(chain && !strcmp(chain, "queue")) && !(dop && !strcmp(dop, "fft"))) {
+                    h->x2_lag = 5;
+                    h->x2_ring = 10;
+                }
             }
             if (const char *env = getenv("WRP_RING")) h->x2_ring = atoi(env);
             if (const char *env = getenv("WRP_LAG")) h->x2_lag = atoi(env);

@@ -124,11 +124,7 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TA = 64 * p.C;                      // tiles (= row groups) per sector
-#ifdef WRP_UNI_WARP_PUBLISH
-    const int TGT_A = TA * NW; // a_done counts warps
-#else
     const int TGT_A = TA;
-#endif
     const int pair_groups = p.C >= 2 ? 128 : 0;   // row groups holding (hh, vv) pairs
     const int total = (p.S + p.lag) * TA;
     int *const a_done = p.ctrl + CTRL_A, *const b_done = p.ctrl + CTRL_A + p.smax;
@@ -172,7 +168,7 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
             if (const int *d = dep_b(f)) spin_until(d, TGT_A);
         }
         s_item[0] = make_int4(f.sa, f.sub, f.slot_a, f.slot_b);
-        s_go[0] = 1;
+        s_go[0] = 3;
     }
     __syncthreads();
     Item it{s_item[0].x, s_item[0].y, s_item[0].z, s_item[0].w};
@@ -194,6 +190,7 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
     uint32_t phase = 0;
     int n = 0;        // index of the current item in this CTA's sequence
     int pending = -1; // sector of a finished range tile whose completion this CTA has not published yet
+    bool rows_late = false; // the current item's rows were requested after its tile (dependency wait)
 
     while (it.sa >= 0) {
         const bool has_a = it.sa < p.S, has_b = it.sa >= p.lag;
@@ -216,20 +213,28 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
         }
         auto publish_next = [&]() {
             if (tid == 0) {
-                bool ready = (!pa || va >= TA) && (!pb || vb >= TGT_A);
-                if (!ready) ready = (!pa || ld_relaxed(pa) >= TA) && (!pb || ld_relaxed(pb) >= TGT_A); // stale probe?
-                if ((p.debug & 16) && cand.sa >= 0 && !ready)
-                    atomicAdd(p.ctrl + ((pb && ld_relaxed(pb) < TGT_A) ? 2 : 1), 1); // [1] ring slot busy, [2] tiles unpublished
+                bool ok_a = !pa || va >= TA, ok_b = !pb || vb >= TGT_A;
+                if (!ok_a) ok_a = ld_relaxed(pa) >= TA; // the early probe may be stale
+                if (!ok_b) ok_b = ld_relaxed(pb) >= TGT_A;
+                if ((p.debug & 16) && cand.sa >= 0) {
+                    if (!ok_a) atomicAdd(p.ctrl + 1, 1); // ring slot still being read
+                    if (!ok_b) atomicAdd(p.ctrl + 2, 1); // tiles of the rows' sector unpublished
+                }
                 s_item[nslot] = make_int4(cand.sa, cand.sub, cand.slot_a, cand.slot_b);
-                s_go[nslot] = ready;
+                s_go[nslot] = (ok_a ? 1 : 0) | (ok_b ? 2 : 0);
             }
         };
+        // (prefetch.global.L2 of the item-after-next's tile, which round-robin dealing makes known two
+        // items ahead, was measured 16-22 % SLOWER — 233k / 215k sectors/s with one / two prefetches per
+        // 64-byte row segment against 276k without: the requests compete with the cp.async stream.)
 
         // ================= Doppler row of this warp: stages 03-08 in energy form =================
         // (see wrp_persistent.cu, DOP == 1, for the derivation)  P = N E - |Y_0|^2 - |Y_{N/2-1}|^2 - |Y_{N/2-2}|^2
         float pw = 0.f;
         if (has_b) {
-            cp_async_wait_group<1>(); // this thread's share of the row (the tile group may still be in flight)
+            // this thread's share of the row; the tile group, committed after it, may still be in flight
+            if (rows_late) cp_async_wait_group<0>();
+            else cp_async_wait_group<1>();
             __syncwarp();
             const uint8_t *row = smem + OFF_ROWS + warp * 4096;
             float2 v[R1B];
@@ -343,8 +348,9 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
             }
         }
         const Item nit{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z, s_item[nslot].w};
-        const bool go = nit.sa >= 0 && s_go[nslot] != 0;
-        if (go) issue_loads_row(nit);
+        const int go_bits = nit.sa >= 0 ? s_go[nslot] : 0;
+        const bool go_a = go_bits & 1, go_b = go_bits & 2; // tile / rows may be fetched now
+        if (go_b) issue_loads_row(nit);
 
         // ================= range tile, second pass =================
         if (has_a) {
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
                 });
             }
             __syncwarp();
-            if (go) issue_loads_tile(nit); // the warp's region is in registers: fetch its share of the next tile
+            if (go_a) issue_loads_tile(nit); // the warp's region is in registers: fetch its share of the next tile
             fft_dit<R, -1>(v);
             {
                 float2 *out = p.x2 + (((size_t)it.slot_a * p.C + ch) * p.half_m + ka) * (size_t)N + col;
@@ -368,30 +374,32 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
                     out[(size_t)(R * kb) * N] = v[kb];
                 });
             }
-#ifdef WRP_UNI_WARP_PUBLISH
-            __syncwarp();
-            if (lane == 0) red_release_add(a_done + it.sa); // this warp's share of the tile (target TA * NW)
-#else
-            pending = it.sa; // published after the next CTA barrier, when these stores have drained
-#endif
-        } else if (go) {
+            // published after the next CTA barrier, when these stores have drained (a red.release per
+            // warp right here was measured 17 % slower: the warp idles until its stores are visible)
+            pending = it.sa;
+        } else if (go_a) {
             issue_loads_tile(nit);
         }
 
-        if (nit.sa < 0 || !go) {
-            // leaving, or the next item's dependency was unmet when probed (it may be a tile this very
-            // CTA still holds unpublished): publish, then thread 0 waits for the counters
+        rows_late = false;
+        if (nit.sa < 0 || !go_a || !go_b) {
+            // leaving, or a dependency of the next item was unmet when probed (it may be a tile this very
+            // CTA still holds unpublished): publish, then thread 0 waits for the counter(s) and the loads
+            // that were held back go out.  A tile whose ring slot was free has already been requested.
             __syncthreads();
             if (pending >= 0 && tid == THREADS - 32) red_release_add(a_done + pending);
             pending = -1;
             if (nit.sa >= 0) {
                 if (tid == 0) {
-                    if (const int *d = dep_a(nit)) spin_until(d, TA);
-                    if (const int *d = dep_b(nit)) spin_until(d, TGT_A);
+                    if (!go_a)
+                        if (const int *d = dep_a(nit)) spin_until(d, TA);
+                    if (!go_b)
+                        if (const int *d = dep_b(nit)) spin_until(d, TGT_A);
                 }
                 __syncthreads();
-                issue_loads_row(nit);
-                issue_loads_tile(nit);
+                if (!go_b) issue_loads_row(nit);
+                if (!go_a) issue_loads_tile(nit);
+                rows_late = go_a && !go_b; // the row group was committed after the tile group
             }
         }
         it = nit;
