@@ -257,6 +257,40 @@ def run_ours(args):
         ms = float(t.item())
     value = world * S * steps / (ms * 1e-3)
 
+    chain_kernel = chain.chain_kernel
+
+    # ---- side figures: the other forms of the same chain on the same resident batch -----------
+    # (environment switches read by libwrp at create/launch time; each gets its own handle)
+    alt = {}
+    if world == 1:
+        for name, env in (("two_kind_queue_energy_form", {"WRP_CHAIN": "queue"}),
+                          ("two_kind_queue_doppler_fft", {"WRP_DOPPLER": "fft"})):
+            saved = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            try:
+                with wrp.RadarChain(local_rank, max_batch=args.host_piece) as alt_chain:
+                    for _ in range(3):
+                        alt_chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a0.record(stream)
+                    for _ in range(steps):
+                        alt_chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
+                    a1.record(stream)
+                    torch.cuda.synchronize()
+                    v = S * steps / (a0.elapsed_time(a1) * 1e-3)
+                    alt[name] = {"value": v, "unit": "sectors/s", "kernel": alt_chain.chain_kernel, "env": env,
+                                 "hbm_frac": v * ALGO_BYTES_C64 / 1e9 / load_peaks()[0]}
+            finally:
+                for k, v0 in saved.items():
+                    if v0 is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v0
+        # leave the default form's products in d_out for the checks below
+        chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+
     # sanity: products finite beyond gate 0
     host = d_out.cpu().numpy()
     if not np.isfinite(host[:, 1:, :]).all():
@@ -333,7 +367,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         if int(prof.n_chain) > 0:
-            kernel, n_k, ms_k = "chain_persistent_kernel", int(prof.n_chain), prof.ms_chain
+            kernel, n_k, ms_k = chain_kernel, int(prof.n_chain), prof.ms_chain
         else:
             kernel, n_k, ms_k = "range_fft_kernel", max(int(prof.n_range), 1), prof.ms_range
         sectors_per_launch = S * steps / n_k
@@ -364,6 +398,10 @@ def run_ours(args):
                               "hbm_frac": wire_resident * ALGO_BYTES_WIRE / 1e9 / peak,
                               "note": "HBM-resident int16 wire sectors: decode pre-pass + chain kernel per chunk of up to 64 sectors"},
             "chain_hbm_frac": chain_gbs / peak,
+            "chain_forms": {"default": {"kernel": chain_kernel,
+                                        "note": "one item = range tile + eight Doppler rows; stages 03-08 in energy "
+                                                "form (Parseval: row energy minus the DC and the two clipped bins)"},
+                            **alt},
             "stress_4096x1024": None if stress is None else dict(stress, hbm_frac=stress["gbs"] / peak),
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -64,7 +64,12 @@ typedef enum {
      * interleaved on every SM; the hand-off between them lives in an L2-resident ring,
      * every other intermediate in registers/shared memory.  Built for M = 1024 or 4096
      * with N = 512 or 1024 (other shapes: WRP_ERR_UNSUPPORTED, use WRP_MODE_STAGED).
-     * (WRP_FUSED_IMPL=v1 in the environment selects the earlier two-kernel form, M = 1024.) */
+     * (WRP_FUSED_IMPL=v1 in the environment selects the earlier two-kernel form, M = 1024.)
+     * Default shape 1024 x 512: one work item = one range tile + eight Doppler rows
+     * (chain_unified_kernel); WRP_CHAIN=queue keeps the two-kind work queue there too.
+     * Stages 03-08 are evaluated in energy form (Parseval: row energy minus the DC bin and the
+     * two clipped bins — same products, no Doppler transform); WRP_DOPPLER=fft runs the literal
+     * transform, shift, clip and |.|^2 instead. */
     WRP_MODE_FUSED = 0,
     /* the reference's kernel cascade stage by stage (rpv2.cu:409-570), every stage
      * materialised in device memory so wrp_dump_stage can return 00iq..10zdr. */
@@ -190,6 +195,11 @@ int wrp_dump_stage(wrp_handle *h, int sector_in_batch, int stage, int channel, v
 
 /* Kernel launches of OUR kernels since creation (bench.py's gpu_launches). */
 unsigned long long wrp_launch_count(const wrp_handle *h);
+
+/* Name of the kernel that carries the chain for this handle's configuration and the current
+ * environment switches ("chain_unified_kernel", "chain_persistent_kernel", "range_fft_kernel",
+ * "staged cascade") — what bench.py's roofline object and the ncu launch list refer to. */
+const char *wrp_chain_kernel_name(const wrp_handle *h);
 
 /* Per-kernel CUDA-event timing. enable: 1 start accumulating / 0 stop. */
 int wrp_profile_enable(wrp_handle *h, int enable);

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "wrp_get_info", "wrp_get_constants", "wrp_process_device", "wrp_process_host",
     "wrp_submit", "wrp_collect", "wrp_alloc_pinned", "wrp_free_pinned", "wrp_dump_stage",
     "wrp_launch_count", "wrp_profile_enable", "wrp_profile_read", "wrp_pack_products",
+    "wrp_chain_kernel_name",
 )
 
 
@@ -119,6 +120,8 @@ def lib():
         L.wrp_dump_stage.argtypes = [vp, ip, ip, ip, vp, C.POINTER(C.c_size_t)]
         L.wrp_launch_count.argtypes = [vp]
         L.wrp_launch_count.restype = C.c_ulonglong
+        L.wrp_chain_kernel_name.argtypes = [vp]
+        L.wrp_chain_kernel_name.restype = C.c_char_p
         L.wrp_profile_enable.argtypes = [vp, ip]
         L.wrp_profile_read.argtypes = [vp, C.POINTER(Profile), ip]
         L.wrp_pack_products.argtypes = [vp, ip, ip, ip, ip, vp, vp]
@@ -232,6 +235,11 @@ class RadarChain:
     @property
     def launch_count(self) -> int:
         return int(lib().wrp_launch_count(self._h))
+
+    @property
+    def chain_kernel(self) -> str:
+        """Name of the kernel that carries the chain for this configuration and environment."""
+        return lib().wrp_chain_kernel_name(self._h).decode()
 
     def constants(self):
         """(hamming[M,N], taps[ma_taps], fft_ma[N] complex) — rpv2.cu:222-281."""

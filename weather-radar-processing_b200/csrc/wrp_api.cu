@@ -162,13 +162,15 @@ static int create_impl(wrp_handle *h)
                 h->x2_ring = 3;
             }
             {
-                // unified-item kernel (default shape, wrp_unified.cu): the rows of sector s are only one
-                // item per sector step behind its last tile, so the lag that keeps dependency waits rare
-                // is one sector larger than for the two-kind queue (measured: 4/8 251k, 5/10 270k, 6/12
-                // 265k sectors/s — 12 slots no longer fit L2 next to the input stream)
+                // unified-item kernel (default shape, wrp_unified.cu): the rows of sector s follow its last
+                // tile by (lag - 1) * 64 C items and a ring slot is reused (ring - lag - 1) * 64 C items
+                // after its last rows, so both margins must cover the ~2 items per CTA between a tile's
+                // start and the publication of its completion.  Measured (sectors/s, 143-sector batches):
+                // 4/8 266k, 5/8 274k, 5/9 280k, 5/10 277k, 6/10 281k, 6/11 275k, 7/11 276k, 6/12 265k
+                // (12 slots = 75 MB no longer fit L2 next to the input stream).
                 const char *chain = getenv("WRP_CHAIN"), *dop = getenv("WRP_DOPPLER");
                 if (wrp::unified_supported(M, N) && !(chain && !strcmp(chain, "queue")) && !(dop && !strcmp(dop, "fft"))) {
-                    h->x2_lag = 5;
+                    h->x2_lag = 6;
                     h->x2_ring = 10;
                 }
             }
@@ -335,6 +337,17 @@ int wrp_get_constants(const wrp_handle *h, float *hamming, float *taps, float *f
 }
 
 unsigned long long wrp_launch_count(const wrp_handle *h) { return h ? h->launches : 0ull; }
+
+const char *wrp_chain_kernel_name(const wrp_handle *h)
+{
+    if (!h) return "";
+    if (h->cfg.mode != WRP_MODE_FUSED) return "staged cascade";
+    if (!h->persistent) return "range_fft_kernel";
+    const char *chain = getenv("WRP_CHAIN"), *dop = getenv("WRP_DOPPLER"), *tc = getenv("WRP_TILE_COLS");
+    const bool unified = wrp::unified_supported(h->cfg.n_rows_M, h->cfg.n_cols_N) && !(chain && !strcmp(chain, "queue")) &&
+                         !(dop && !strcmp(dop, "fft")) && !(tc && atoi(tc) == 4) && !(getenv("WRP_DISCARD") && atoi(getenv("WRP_DISCARD"))) && h->l2_window == 0;
+    return unified ? "chain_unified_kernel" : "chain_persistent_kernel";
+}
 
 // ---- profiling ------------------------------------------------------------------------
 static cudaEvent_t get_event(wrp_handle *h)
