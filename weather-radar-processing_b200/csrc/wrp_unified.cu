@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
 
     // every item's loads are two cp.async groups per thread, committed in this order: row, tile part
     auto issue_loads_row = [&](const Item &x) {
+        // (one 4 KiB cp.async.bulk per warp instead of eight cp.async per lane: measured neutral, 279.6k vs 280.1k)
         if (x.sa >= p.lag) uni_issue_row(x, p, smem, pair_groups, warp, lane);
         cp_async_commit();
     };
