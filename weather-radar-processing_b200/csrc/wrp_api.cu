@@ -168,8 +168,7 @@ static int create_impl(wrp_handle *h)
                 // start and the publication of its completion.  Measured (sectors/s, 143-sector batches):
                 // 4/8 266k, 5/8 274k, 5/9 280k, 5/10 277k, 6/10 281k, 6/11 275k, 7/11 276k, 6/12 265k
                 // (12 slots = 75 MB no longer fit L2 next to the input stream).
-                const char *chain = getenv("WRP_CHAIN"), *dop = getenv("WRP_DOPPLER");
-                if (wrp::unified_supported(M, N) && !(chain && !strcmp(chain, "queue")) && !(dop && !strcmp(dop, "fft"))) {
+                if (wrp::chain_uses_unified_kernel(M, N, 0)) {
                     h->x2_lag = 6;
                     h->x2_ring = 10;
                 }
@@ -343,9 +342,7 @@ const char *wrp_chain_kernel_name(const wrp_handle *h)
     if (!h) return "";
     if (h->cfg.mode != WRP_MODE_FUSED) return "staged cascade";
     if (!h->persistent) return "range_fft_kernel";
-    const char *chain = getenv("WRP_CHAIN"), *dop = getenv("WRP_DOPPLER"), *tc = getenv("WRP_TILE_COLS");
-    const bool unified = wrp::unified_supported(h->cfg.n_rows_M, h->cfg.n_cols_N) && !(chain && !strcmp(chain, "queue")) &&
-                         !(dop && !strcmp(dop, "fft")) && !(tc && atoi(tc) == 4) && !(getenv("WRP_DISCARD") && atoi(getenv("WRP_DISCARD"))) && h->l2_window == 0;
+    const bool unified = wrp::chain_uses_unified_kernel(h->cfg.n_rows_M, h->cfg.n_cols_N, h->l2_window);
     return unified ? "chain_unified_kernel" : "chain_persistent_kernel";
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace wrp {
@@ -34,6 +35,12 @@ struct PersistParams {
     float range_res, calib, taps_sum;
 };
 constexpr int CTRL_A = 32;
+
+// Which kernel carries a fused batch of this shape under the current environment switches
+// (WRP_CHAIN=queue, WRP_DOPPLER=fft, WRP_TILE_COLS=4, WRP_DISCARD=1 and an L2 access-policy window
+// all select the two-kind queue of wrp_persistent.cu).  The one place that decides: the launch,
+// the lag / ring defaults and wrp_chain_kernel_name all ask here.
+bool chain_uses_unified_kernel(int M, int N, size_t l2_window_bytes);
 
 // wrp_unified.cu: M = 1024, N = 512 only.  p.tiles_a, p.pair_blocks are ignored (recomputed).
 bool unified_supported(int M, int N);

@@ -742,6 +742,20 @@ static int tile_cols(int M)
     return M == 4096 ? 4 : t;
 }
 
+static bool env_is(const char *name, const char *value)
+{
+    const char *v = getenv(name);
+    return v && !strcmp(v, value);
+}
+static bool doppler_fft_requested() { return env_is("WRP_DOPPLER", "fft"); }
+static bool discard_requested() { return getenv("WRP_DISCARD") && atoi(getenv("WRP_DISCARD")) != 0; }
+
+bool chain_uses_unified_kernel(int M, int N, size_t l2_window_bytes)
+{
+    return unified_supported(M, N) && tile_cols(M) == 8 && !doppler_fft_requested() && !discard_requested() &&
+           l2_window_bytes == 0 && !env_is("WRP_CHAIN", "queue");
+}
+
 cudaError_t persistent_setup()
 {
     cudaError_t e;
@@ -803,11 +817,10 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.smax = smax;
     // (M = 4096: the hand-off of even one sector exceeds L2, so protecting it buys nothing; measured 5 % slower)
     p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : (M == 1024);
-    p.discard = getenv("WRP_DISCARD") ? atoi(getenv("WRP_DISCARD")) : 0; // -2 % throughput; evict-first already keeps the ring in L2
+    p.discard = discard_requested(); // -2 % throughput; evict-first already keeps the ring in L2
     p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
     // Doppler blocks: energy form (default) or the literal two-pass transform (WRP_DOPPLER=fft)
-    const char *dop = getenv("WRP_DOPPLER");
-    const bool doppler_fft = dop && !strcmp(dop, "fft");
+    const bool doppler_fft = doppler_fft_requested();
     p.range_res = range_res;
     p.calib = calib;
     p.taps_sum = taps_sum;
@@ -816,12 +829,7 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     if (e != cudaSuccess) return e;
     // Default sector shape: the unified-item kernel (one item = range tile + eight Doppler rows,
     // wrp_unified.cu).  WRP_CHAIN=queue keeps the two-kind work queue of this file.
-    {
-        const char *chain = getenv("WRP_CHAIN");
-        if (unified_supported(M, N) && T == 8 && !doppler_fft && !p.discard && l2_window_bytes == 0 &&
-            !(chain && !strcmp(chain, "queue")))
-            return launch_unified(p, sm_count, st);
-    }
+    if (chain_uses_unified_kernel(M, N, l2_window_bytes)) return launch_unified(p, sm_count, st);
     int grid = (16 / NW) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
 
