@@ -37,6 +37,7 @@ def run_one(args, cfg):
             b.synchronize(); ts.append(a.elapsed_time(b))
         ts.sort()
         ms = ts[len(ts) // 2]
+        kernel = ch.chain_kernel
     o = out.cpu().numpy()
     dz = dr = 0.0
     for s in range(min(2, S)):
@@ -47,7 +48,7 @@ def run_one(args, cfg):
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6450.6
     bytes_sector = 3 * M * N * 8 + (M // 2) * 8
     sps = S / (ms * 1e-3)
-    print(json.dumps({"cfg": cfg, "shape": args.shape, "sectors": S, "ms": round(ms, 4), "min_ms": round(ts[0], 4),
+    print(json.dumps({"cfg": cfg, "kernel": kernel, "shape": args.shape, "sectors": S, "ms": round(ms, 4), "min_ms": round(ts[0], 4),
                       "sectors_per_s": round(sps), "hbm_frac": round(sps * bytes_sector / (peak * 1e9), 4),
                       "max_dZdB": dz, "max_dZDR": dr}), flush=True)
 
