@@ -6,7 +6,6 @@ HOST     := $(PKG)/host
 NVCC     ?= nvcc
 CXX      := g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xptxas -v --use_fast_math
 NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC
 LIB      := $(PKG)/libwrp.so
 OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_unified.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
@@ -41,7 +40,14 @@ $(LIB): $(OBJS)
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
+# Experimental, not validated on a GPU: the pair kernel (csrc/experimental/wrp_pair.cu) linked in
+# place of wrp_unified.o.  A/B it with  WRP_LIB=$$PWD/tools/libwrp_pair.so python tools/ab.py ...
+pair: $(LIB)
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/experimental/wrp_pair.cu -o $(CSRC)/experimental/wrp_pair.o
+	$(NVCC) $(ARCH) -shared -o tools/libwrp_pair.so $(filter-out $(CSRC)/wrp_unified.o,$(OBJS)) $(CSRC)/experimental/wrp_pair.o -cudart static
+	python tools/check_sass.py tools/libwrp_pair.so
+
 clean:
 	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(HOSTBINS)
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean pair
