@@ -217,3 +217,35 @@ def test_energy_form_of_the_doppler_stage_on_oracle_spectra(oracle, wrp):
     # the subtraction never cancels more than ~3/4 of the row energy: the Doppler window spreads
     # any line over three bins, only bin 0 and two edge bins are removed
     assert np.max(removed / (np.float32(N) * energy)) < 0.9
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+def test_pruned_dft_decomposition_used_by_the_kernels(n):
+    """The algebra behind `dft_bins012` (wrp_fft.cuh) and the per-lane factors of the energy form:
+    with j = 32 a + l, Doppler bin N/2 - m of the un-normalised inverse transform is
+    sum_l (-1)^l e^{-2 pi i l m / N} D_m(l), D_m(l) = bin m of the forward (N/32)-point DFT over a, and
+    bins 0, 1, 2 of that DFT follow from a decimation-in-frequency network pruned to three outputs."""
+    rng = np.random.default_rng(n)
+    r = n // 32
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    y = np.fft.ifft(x) * n  # Y_b = sum_j x_j e^{+2 pi i j b / N}
+    xa = x.reshape(r, 32)   # xa[a][l] = x[32 a + l]
+    w = np.exp(-2j * np.pi / r)
+    s, d = xa[:r // 2] + xa[r // 2:], xa[:r // 2] - xa[r // 2:]
+    g1 = d[:r // 4] - 1j * d[r // 4:]
+    b1 = sum(g1[a] * w ** a for a in range(r // 4))
+    ss, sd = s[:r // 4] + s[r // 4:], s[:r // 4] - s[r // 4:]
+    b0 = ss.sum(axis=0)
+    g2 = sd[:r // 8] - 1j * sd[r // 8:]
+    b2 = sum(g2[a] * (w * w) ** a for a in range(r // 8))
+    full = np.fft.fft(xa, axis=0)  # forward DFT over a, per lane
+    assert np.allclose(b0, full[0]) and np.allclose(b1, full[1]) and np.allclose(b2, full[2])
+    lane = np.arange(32)
+    for m, bm in ((1, b1), (2, b2)):
+        t = (-1.0) ** lane * np.exp(-2j * np.pi * lane * m / n)
+        assert abs((t * bm).sum() - y[n // 2 - m]) < 1e-9 * np.abs(y).max()
+    assert abs(b0.sum() - y[0]) < 1e-9 * np.abs(y).max()
+    power = n * np.sum(np.abs(x) ** 2) - abs(y[0]) ** 2 - abs(y[n // 2 - 1]) ** 2 - abs(y[n // 2 - 2]) ** 2
+    keep = np.ones(n, bool)
+    keep[[0, n // 2 - 1, n // 2 - 2]] = False
+    assert abs(power - np.sum(np.abs(y[keep]) ** 2)) < 1e-9 * power
