@@ -144,7 +144,7 @@ def run_reference(args):
     synth = importlib.import_module("weather-radar-processing_b200.synth")
     cores = os.cpu_count() or 1
     exe = os.path.join(ROOT, "oracle", "_ref", "read_single_ref")
-    per_proc = 2
+    per_proc = 8  # amortises the reference's start-up (window tables, plans: ~35 ms) to ~4 % of a process's run
     steps, warmup = args.steps, args.warmup
     if os.path.exists(exe):
         kind = "reference"
