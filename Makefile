@@ -50,4 +50,11 @@ pair: $(LIB)
 clean:
 	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(HOSTBINS)
 
-.PHONY: all oracle clean pair
+# Experimental, not validated on a GPU: chain_unified_kernel with the exchange rendezvous as a
+# split-phase mbarrier (-DWRP_UNI_SPLIT_BARRIER); the default build is byte-identical without it.
+split: $(LIB)
+	$(NVCC) $(NVFLAGS) -DWRP_UNI_SPLIT_BARRIER -c $(CSRC)/wrp_unified.cu -o $(CSRC)/experimental/wrp_unified_split.o
+	$(NVCC) $(ARCH) -shared -o tools/libwrp_split.so $(filter-out $(CSRC)/wrp_unified.o,$(OBJS)) $(CSRC)/experimental/wrp_unified_split.o -cudart static
+	python tools/check_sass.py tools/libwrp_split.so
+
+.PHONY: all oracle clean pair split

@@ -108,6 +108,13 @@ __device__ __forceinline__ void spin_until(const int *p, int target)
     while (ld_acquire(p) < target) __nanosleep(100);
 }
 
+// split-phase CTA rendezvous: arrive now (release), wait later (acquire) — work in between overlaps
+// the time the slower warps still need
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // cp.async groups: the calling thread's copies since its previous commit form one group
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait_group()

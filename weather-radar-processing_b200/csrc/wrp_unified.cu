@@ -121,6 +121,12 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
     __shared__ int4 s_item[2];             // published items, by item parity
     __shared__ int s_go[2];                // ... and whether their dependencies were met when probed
     __shared__ float p_row[2][NW];         // row powers of the current item, by item parity
+#ifdef WRP_UNI_SPLIT_BARRIER
+    // EXPERIMENT (not validated on a GPU; the default build is unaffected): the exchange rendezvous as a
+    // split-phase mbarrier — arrive after the exchange stores, do the Doppler row's arithmetic, then wait
+    __shared__ __align__(8) uint64_t xbar;
+    uint32_t xphase = 0;
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TA = 64 * p.C;                      // tiles (= row groups) per sector
@@ -159,6 +165,9 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
     int claimed_next = 0; // thread 0: queue index of the item after the current one
     if (tid == 0) {
         mbar_init(&mbar, THREADS);
+#ifdef WRP_UNI_SPLIT_BARRIER
+        mbar_init(&xbar, THREADS);
+#endif
         const int first = blockIdx.x;
         claimed_next = first + gridDim.x;
         Item f{-1, 0, 0, 0};
@@ -232,26 +241,28 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
         // ================= Doppler row of this warp: stages 03-08 in energy form =================
         // (see wrp_persistent.cu, DOP == 1, for the derivation)  P = N E - |Y_0|^2 - |Y_{N/2-1}|^2 - |Y_{N/2-2}|^2
         float pw = 0.f;
-        if (has_b) {
+        float2 rv[R1B]; // the warp's Doppler row, lane l holds x[32 a + l]
+        auto row_load = [&]() {
             // this thread's share of the row; the tile group, committed after it, may still be in flight
             if (rows_late) cp_async_wait_group<0>();
             else cp_async_wait_group<1>();
             __syncwarp();
             const uint8_t *row = smem + OFF_ROWS + warp * 4096;
-            float2 v[R1B];
             static_for<R1B>([&](auto ai) {
                 constexpr int a = decltype(ai)::value;
-                v[a] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
+                rv[a] = *reinterpret_cast<const float2 *>(row + (32 * a + lane) * 8);
             });
+        };
+        auto row_math = [&]() {
             const float4 tl = *reinterpret_cast<const float4 *>(smem + OFF_TL + lane * 16);
             float2 e2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             static_for<R1B>([&](auto ai) {
                 constexpr int a = decltype(ai)::value;
-                e2[a & 1] = cfma2(v[a], v[a], e2[a & 1]);
+                e2[a & 1] = cfma2(rv[a], rv[a], e2[a & 1]);
             });
             const float2 es = cadd(e2[0], e2[1]);
             float2 b0, b1, b2;
-            dft_bins012<R1B>(v, b0, b1, b2);
+            dft_bins012<R1B>(rv, b0, b1, b2);
             const float2 y1 = cmul(b1, make_float2(tl.x, tl.y)), y2 = cmul(b2, make_float2(tl.z, tl.w));
             float r[7] = {es.x + es.y, b0.x, b0.y, y1.x, y1.y, y2.x, y2.y};
 #pragma unroll
@@ -264,7 +275,13 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
             for (int k = 2; k < 7; ++k) removed = fmaf(r[k], r[k], removed);
             pw = fmaxf(fmaf((float)N, r[0], -removed), 0.f) * p.taps_sum; // stages 05-08: x sum of the taps
             if (lane == 0) p_row[n & 1][warp] = pw;
+        };
+#ifndef WRP_UNI_SPLIT_BARRIER
+        if (has_b) {
+            row_load();
+            row_math();
         }
+#endif
 
         // ================= range tile, first pass =================
         const int c = tid % T, b = tid / T;
@@ -326,17 +343,17 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
         } else {
             publish_next();
         }
+#ifdef WRP_UNI_SPLIT_BARRIER
+        if (has_b) row_load(); // in registers before the arrival, so b_done may follow the wait
+        mbar_arrive(&xbar);
+        if (has_b) row_math(); // overlaps the wait for the slower warps
+        mbar_wait(&xbar, xphase);
+        xphase ^= 1;
+#else
         __syncthreads(); // the exchange — and the one rendezvous of the item
+#endif
 
-        // ---- right after the barrier: publications, products, the next item's Doppler row ----
-        if (pending >= 0 && tid == THREADS - 32) red_release_add(a_done + pending); // every warp's x2 stores precede the barrier
-        pending = -1;
-        if (has_b) {
-            const int sb = it.sa - p.lag;
-            // every warp's row has landed: the ring rows are free.  (Counting per warp at the top of the
-            // item instead — eight atomics on one address per item — was measured 11 % slower: the
-            // counter becomes an L2 hot spot and the dependency waits double.)
-            if (tid == THREADS - 64) atomicAdd(b_done + sb, 1);
+        auto write_products = [&](int sb) {
             if (lane == 0) {
                 int chn, gate;
                 (void)uni_row(p, it.slot_b, it.sub, pair_groups, warp, chn, gate);
@@ -350,11 +367,30 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
                         make_float2(10.f * log10f(z), pair ? 10.f * (log10f(pw) - log10f(p_row[n & 1][warp + 1])) : 0.f);
                 }
             }
+        };
+        // ---- right after the barrier: publications, products, the next item's Doppler row ----
+        if (pending >= 0 && tid == THREADS - 32) red_release_add(a_done + pending); // every warp's x2 stores precede the barrier
+        pending = -1;
+        if (has_b) {
+            const int sb = it.sa - p.lag;
+            // every warp's row has landed: the ring rows are free.  (Counting per warp at the top of the
+            // item instead — eight atomics on one address per item — was measured 11 % slower: the
+            // counter becomes an L2 hot spot and the dependency waits double.)
+            if (tid == THREADS - 64) atomicAdd(b_done + sb, 1);
+#ifndef WRP_UNI_SPLIT_BARRIER
+            write_products(sb);
+#endif
         }
         const Item nit{s_item[nslot].x, s_item[nslot].y, s_item[nslot].z, s_item[nslot].w};
         const int go_bits = nit.sa >= 0 ? s_go[nslot] : 0;
         const bool go_a = go_bits & 1, go_b = go_bits & 2; // tile / rows may be fetched now
         if (go_b) issue_loads_row(nit);
+#ifdef WRP_UNI_SPLIT_BARRIER
+        if (has_b) { // p_row of the neighbouring warp was written after its arrival: meet it first
+            bar_sync(1 + (warp >> 1), 64);
+            write_products(it.sa - p.lag);
+        }
+#endif
 
         // ================= range tile, second pass =================
         if (has_a) {
