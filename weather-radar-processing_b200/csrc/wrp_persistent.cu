@@ -1,4 +1,6 @@
-// wrp_persistent.cu — the fused chain as ONE persistent kernel per batch (sm_100a).
+// wrp_persistent.cu — the fused chain as ONE persistent kernel per batch (sm_100a): the two-kind
+// work queue.  Carries N = 1024 and M = 4096; the default 1024 x 512 sector runs on wrp_unified.cu
+// (one item = tile + rows) unless WRP_CHAIN=queue or WRP_DOPPLER=fft select this file.
 //
 // Work items, handed out in queue order by an atomic counter:
 //   A(s, tile)  range tile: T (= 8) adjacent columns x 1024 rows of one (sector, channel) plane.
@@ -9,6 +11,9 @@
 //   B(s, block) Doppler block: 16 rows (8 gates x hh,vv or 16 gates of vh) of the x2 ring ->
 //               mean removal, inverse DFT, shift, clip, |.|^2, moving-average power, ZdB/ZDR
 //               (stages 03-10; replaces rpv2.cu:93-213, 434-566).  Rows are warp-private.
+//               DOP = 1 (default): stages 03-08 in energy form — row energy minus the DC bin and the
+//               two clipped bins (Parseval), one pass over the row; DOP = 0 (WRP_DOPPLER=fft): the
+//               literal two-pass transform.
 // The queue interleaves A(t) with B(t - lag), so the x2 hand-off lives in a small ring
 // (ring x 6 MiB) that never leaves L2, there is no kernel boundary between the phases, and
 // DRAM-heavy A items overlap compute-heavy B items on every SM.
