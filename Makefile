@@ -50,11 +50,21 @@ pair: $(LIB)
 clean:
 	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(HOSTBINS)
 
-# Experimental, not validated on a GPU: chain_unified_kernel with the exchange rendezvous as a
-# split-phase mbarrier (-DWRP_UNI_SPLIT_BARRIER); the default build is byte-identical without it.
-split: $(LIB)
-	$(NVCC) $(NVFLAGS) -DWRP_UNI_SPLIT_BARRIER -c $(CSRC)/wrp_unified.cu -o $(CSRC)/experimental/wrp_unified_split.o
-	$(NVCC) $(ARCH) -shared -o tools/libwrp_split.so $(filter-out $(CSRC)/wrp_unified.o,$(OBJS)) $(CSRC)/experimental/wrp_unified_split.o -cudart static
-	python tools/check_sass.py tools/libwrp_split.so
+# Experimental variants of chain_unified_kernel, none validated on a GPU yet (the default build is
+# byte-identical without the guarded code): each becomes tools/libwrp_<name>.so for tools/ab.py.
+#   split      exchange rendezvous as a split-phase mbarrier, Doppler arithmetic in between
+#   x2last     x2 hand-off stores carry an L2 evict-last policy
+#   rowsfirst  ring rows are read with an L2 evict-first policy (dead after the read)
+#   l2both     x2last + rowsfirst
+VARIANTS := split x2last rowsfirst l2both
+FLAGS_split     := -DWRP_UNI_SPLIT_BARRIER
+FLAGS_x2last    := -DWRP_UNI_X2_EVICT_LAST
+FLAGS_rowsfirst := -DWRP_UNI_ROWS_EVICT_FIRST
+FLAGS_l2both    := -DWRP_UNI_X2_EVICT_LAST -DWRP_UNI_ROWS_EVICT_FIRST
+variants: $(addprefix tools/libwrp_,$(addsuffix .so,$(VARIANTS)))
+tools/libwrp_%.so: $(LIB) $(CSRC)/wrp_unified.cu
+	$(NVCC) $(NVFLAGS) $(FLAGS_$*) -c $(CSRC)/wrp_unified.cu -o $(CSRC)/experimental/wrp_unified_$*.o
+	$(NVCC) $(ARCH) -shared -o $@ $(filter-out $(CSRC)/wrp_unified.o,$(OBJS)) $(CSRC)/experimental/wrp_unified_$*.o -cudart static
+	python tools/check_sass.py $@
 
-.PHONY: all oracle clean pair split
+.PHONY: all oracle clean pair variants

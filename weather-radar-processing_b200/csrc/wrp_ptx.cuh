@@ -108,6 +108,18 @@ __device__ __forceinline__ void spin_until(const int *p, int target)
     while (ld_acquire(p) < target) __nanosleep(100);
 }
 
+// L2 evict-last policy and an 8-byte store carrying it (experiments on keeping the x2 ring resident)
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_global_hint(float2 *ptr, float2 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(ptr), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+
 // split-phase CTA rendezvous: arrive now (release), wait later (acquire) — work in between overlaps
 // the time the slower warps still need
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)

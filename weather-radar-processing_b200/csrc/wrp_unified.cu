@@ -85,8 +85,16 @@ __device__ __forceinline__ void uni_issue_row(const Item &it, const PersistParam
     int chn, gate;
     const uint8_t *src = uni_row(p, it.slot_b, it.sub, pair_groups, warp, chn, gate) + lane * 16;
     uint8_t *dst = smem + uni::OFF_ROWS + warp * 4096 + lane * 16;
+#ifdef WRP_UNI_ROWS_EVICT_FIRST
+    // EXPERIMENT (not validated on a GPU): a ring row is dead once it has been read — let L2 drop it first
+    const uint64_t pol = policy_evict_first();
+    const uint32_t d = opaque_smem_addr(dst, p.zero);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cp_async16_evict_first(d + k * 512, src + k * 512, pol);
+#else
 #pragma unroll
     for (int k = 0; k < 8; ++k) cp_async16(dst + k * 512, src + k * 512);
+#endif
 }
 
 // the warp's 8 KiB region (rows [128 warp, +128)) of the range tile of item `it`, then one arrival
@@ -411,7 +419,12 @@ __global__ void __launch_bounds__(uni::THREADS, 2) chain_unified_kernel(const Pe
                 float2 *out = p.x2 + (((size_t)it.slot_a * p.C + ch) * p.half_m + ka) * (size_t)N + col;
                 static_for<R / 2>([&](auto ki) { // rows k = ka + 32 kb < M/2
                     constexpr int kb = decltype(ki)::value;
+#ifdef WRP_UNI_X2_EVICT_LAST
+                    // EXPERIMENT (not validated on a GPU): keep the hand-off in L2 against the input stream
+                    st_global_hint(out + (size_t)(R * kb) * N, v[kb], policy_evict_last());
+#else
                     out[(size_t)(R * kb) * N] = v[kb];
+#endif
                 });
             }
             // published after the next CTA barrier, when these stores have drained (a red.release per
