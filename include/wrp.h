@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define WRP_VERSION 100 /* 1.0.0 */
+#define WRP_VERSION 200 /* 2.0.0: wrp_config grew (doppler_form .. debug), streaming chain kernel, volume entry points */
 
 typedef enum {
     WRP_OK = 0,
@@ -59,22 +59,36 @@ typedef enum {
 } wrp_input_fmt;
 
 typedef enum {
-    /* one persistent kernel per batch: range-FFT tiles (window on load) and Doppler blocks
-     * (mean removal, shift/clip, |.|^2, moving-average power, dB products in the epilogue)
-     * interleaved on every SM; the hand-off between them lives in an L2-resident ring,
-     * every other intermediate in registers/shared memory.  Built for M = 1024 or 4096
-     * with N = 512 or 1024 (other shapes: WRP_ERR_UNSUPPORTED, use WRP_MODE_STAGED).
-     * (WRP_FUSED_IMPL=v1 in the environment selects the earlier two-kernel form, M = 1024.)
-     * Default shape 1024 x 512: one work item = one range tile + eight Doppler rows
-     * (chain_unified_kernel); WRP_CHAIN=queue keeps the two-kind work queue there too.
-     * Stages 03-08 are evaluated in energy form (Parseval: row energy minus the DC bin and the
-     * two clipped bins — same products, no Doppler transform); WRP_DOPPLER=fft runs the literal
-     * transform, shift, clip and |.|^2 instead. */
+    /* ONE persistent kernel per batch, every intermediate in registers / shared memory
+     * (chain_stream_kernel, csrc/wrp_stream.cu): a CTA walks the range tiles of one (sector,
+     * channel) plane after another — window on load, radix-32 x radix-32 range FFT — and folds every
+     * tile's rows k < M/2 straight into the per-gate sums that stages 03-08 reduce to in energy form
+     * (Parseval: row energy minus the DC bin and the two clipped bins); ZdB/ZDR when a sector's hh
+     * and vv planes are complete.  There is no range -> Doppler hand-off buffer and no CTA ever
+     * waits for another.  Built for M = 1024 (planar or wire input, decode on the load path) and
+     * M = 4096 (planar; wire goes through a decode pre-pass), any power-of-two N in [64, 8192].
+     * doppler_form = WRP_DOPPLER_FFT or chain_impl = WRP_CHAIN_QUEUE select the two-kind work queue
+     * (chain_persistent_kernel: range tiles + Doppler blocks with an L2-resident hand-off ring,
+     * M = 1024 / 4096, N = 512 / 1024), which can run the literal Doppler transform, shift, clip
+     * and |.|^2.  Other shapes: WRP_ERR_UNSUPPORTED, use WRP_MODE_STAGED. */
     WRP_MODE_FUSED = 0,
     /* the reference's kernel cascade stage by stage (rpv2.cu:409-570), every stage
      * materialised in device memory so wrp_dump_stage can return 00iq..10zdr. */
     WRP_MODE_STAGED = 1
 } wrp_mode;
+
+/* How the fused kernels evaluate stages 03-08 (rpv2.cu:93-197). */
+typedef enum {
+    WRP_DOPPLER_ENERGY = 0, /* Parseval form: same products, no Doppler transform (default)      */
+    WRP_DOPPLER_FFT = 1     /* literal mean removal, transform, shift, clip, |.|^2, row sum      */
+} wrp_doppler_form;
+
+/* Which fused kernel family carries the chain. */
+typedef enum {
+    WRP_CHAIN_AUTO = 0,   /* streaming kernel when the shape and doppler_form allow, else the queue */
+    WRP_CHAIN_QUEUE = 1,  /* two-kind work queue with the L2-resident x2 ring (round-1 product path) */
+    WRP_CHAIN_V1 = 2      /* two kernels per chunk (range_fft_kernel + doppler_kernel), M = 1024     */
+} wrp_chain_impl;
 
 /* Stage ids of the reference's dump files. */
 typedef enum {
@@ -105,6 +119,13 @@ typedef struct {
     int input_fmt;     /* wrp_input_fmt                                                  */
     int mode;          /* wrp_mode                                                       */
     int max_batch;     /* largest n_sectors of one process/submit call (ring slot size)  */
+    int doppler_form;  /* wrp_doppler_form (fused mode)                                  */
+    int chain_impl;    /* wrp_chain_impl (fused mode)                                    */
+    int x2_lag;        /* queue kernel: Doppler blocks trail the range tiles by this many sectors (0 = default) */
+    int x2_ring;       /* queue kernel: sector slots of the hand-off ring (0 = default)  */
+    int evict_first;   /* queue kernel: stream the input through L2 evict-first (-1 = default, 0 off, 1 on) */
+    int debug;         /* development switches: 16 = dependency counters of the queue kernel on stderr;
+                        * 32 = planar input uses the wire path's work partition (bit-identical sums, tests) */
 } wrp_config;
 
 typedef struct wrp_handle wrp_handle;
@@ -116,7 +137,7 @@ typedef struct {
     int l2_bytes;
     size_t input_bytes_per_sector;  /* in the configured input_fmt                       */
     size_t output_floats_per_sector; /* 2 * M/2                                          */
-    size_t intermediate_bytes_per_sector; /* range->Doppler hand-off kept in L2          */
+    size_t intermediate_bytes_per_sector; /* range->Doppler hand-off kept in L2 (0: streaming kernel) */
     int chunk_sectors;              /* sectors per launch (persistent kernel) or per kernel pair (v1) */
     int kernels_per_chunk;          /* launches of our kernels per chunk                 */
 } wrp_info;
@@ -134,7 +155,8 @@ typedef struct {
 } wrp_profile;
 
 /* Fill cfg with the reference's defaults (rpv2.cu:38-45): 1024 x 512 x 3, 7 taps,
- * 30 m, 1941.05, 3 streams, planar input, fused mode, max_batch 64. */
+ * 30 m, 1941.05, 3 streams, planar input, fused mode (streaming kernel, energy form), max_batch 8.
+ * ALWAYS start from this call: fields added in later versions get their defaults here. */
 void wrp_default_config(wrp_config *cfg);
 
 /* Replaces generate_constants + prepare_arys + initialize_streams
@@ -196,10 +218,18 @@ int wrp_dump_stage(wrp_handle *h, int sector_in_batch, int stage, int channel, v
 /* Kernel launches of OUR kernels since creation (bench.py's gpu_launches). */
 unsigned long long wrp_launch_count(const wrp_handle *h);
 
-/* Name of the kernel that carries the chain for this handle's configuration and the current
- * environment switches ("chain_unified_kernel", "chain_persistent_kernel", "range_fft_kernel",
- * "staged cascade") — what bench.py's roofline object and the ncu launch list refer to. */
+/* Name of the kernel that carries the chain for this handle's configuration
+ * ("chain_stream_kernel", "chain_persistent_kernel", "range_fft_kernel", "staged cascade") —
+ * what bench.py's roofline object and the ncu launch list refer to. */
 const char *wrp_chain_kernel_name(const wrp_handle *h);
+
+/* Diagnostic tap of the streaming kernel (tests): while dev_x2 is non-NULL every launch also
+ * stores the range-FFT rows k < M/2 it folds — stage 02 as the PRODUCT kernel computes it — to
+ * dev_x2[sector][channel][M/2][N] complex float (device memory owned by the caller, large enough
+ * for the batches processed).  The reference's equivalent is the commented-out dump block inside
+ * its running chain (rpv2.cu:582-603).  NULL switches the tap off.  WRP_ERR_STATE if the handle
+ * does not run the streaming kernel. */
+int wrp_set_stage02_tap(wrp_handle *h, void *dev_x2);
 
 /* Per-kernel CUDA-event timing. enable: 1 start accumulating / 0 stop. */
 int wrp_profile_enable(wrp_handle *h, int enable);

@@ -28,6 +28,11 @@ FMT_C64_PLANAR = 0
 FMT_WIRE_I16BE = 1
 MODE_FUSED = 0
 MODE_STAGED = 1
+DOPPLER_ENERGY = 0
+DOPPLER_FFT = 1
+CHAIN_AUTO = 0
+CHAIN_QUEUE = 1
+CHAIN_V1 = 2
 
 STAGE_IDS = {
     "00iq": 0, "01hamm": 1, "02fft1": 2, "03fft2": 3, "04abs": 4, "05fft3": 5,
@@ -41,7 +46,7 @@ EXPORTED_SYMBOLS = (
     "wrp_get_info", "wrp_get_constants", "wrp_process_device", "wrp_process_host",
     "wrp_submit", "wrp_collect", "wrp_alloc_pinned", "wrp_free_pinned", "wrp_dump_stage",
     "wrp_launch_count", "wrp_profile_enable", "wrp_profile_read", "wrp_pack_products",
-    "wrp_chain_kernel_name",
+    "wrp_chain_kernel_name", "wrp_set_stage02_tap",
 )
 
 
@@ -56,6 +61,8 @@ class Config(C.Structure):
         ("n_rows_M", C.c_int), ("n_cols_N", C.c_int), ("n_channels", C.c_int),
         ("n_streams", C.c_int), ("ma_taps", C.c_int), ("range_res_m", C.c_float),
         ("calib", C.c_float), ("input_fmt", C.c_int), ("mode", C.c_int), ("max_batch", C.c_int),
+        ("doppler_form", C.c_int), ("chain_impl", C.c_int), ("x2_lag", C.c_int), ("x2_ring", C.c_int),
+        ("evict_first", C.c_int), ("debug", C.c_int),
     ]
 
 
@@ -122,6 +129,7 @@ def lib():
         L.wrp_launch_count.restype = C.c_ulonglong
         L.wrp_chain_kernel_name.argtypes = [vp]
         L.wrp_chain_kernel_name.restype = C.c_char_p
+        L.wrp_set_stage02_tap.argtypes = [vp, vp]
         L.wrp_profile_enable.argtypes = [vp, ip]
         L.wrp_profile_read.argtypes = [vp, C.POINTER(Profile), ip]
         L.wrp_pack_products.argtypes = [vp, ip, ip, ip, ip, vp, vp]
@@ -238,8 +246,13 @@ class RadarChain:
 
     @property
     def chain_kernel(self) -> str:
-        """Name of the kernel that carries the chain for this configuration and environment."""
+        """Name of the kernel that carries the chain for this configuration."""
         return lib().wrp_chain_kernel_name(self._h).decode()
+
+    def set_stage02_tap(self, dev_ptr: int | None):
+        """Streaming kernel only: also store the range-FFT rows k < M/2 it folds to device memory
+        [sector][channel][M/2][N] complex64 at dev_ptr (None switches the tap off)."""
+        self._check(lib().wrp_set_stage02_tap(self._h, dev_ptr))
 
     def constants(self):
         """(hamming[M,N], taps[ma_taps], fft_ma[N] complex) — rpv2.cu:222-281."""

@@ -10,7 +10,9 @@
 // d_tmp race cannot occur.
 #include "wrp_internal.h"
 #include "wrp_chain_params.h"
+#include "wrp_stream.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,6 +67,12 @@ void wrp_default_config(wrp_config *cfg)
     cfg->input_fmt = WRP_FMT_C64_PLANAR;
     cfg->mode = WRP_MODE_FUSED;
     cfg->max_batch = 8;
+    cfg->doppler_form = WRP_DOPPLER_ENERGY;
+    cfg->chain_impl = WRP_CHAIN_AUTO;
+    cfg->x2_lag = 0;
+    cfg->x2_ring = 0;
+    cfg->evict_first = -1;
+    cfg->debug = 0;
 }
 
 const char *wrp_last_error(const wrp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -82,10 +90,11 @@ static void free_all(wrp_handle *h)
     F(h->fused.tw_b);
     F(h->fused.wr4);
     F(h->fused.tw4);
+    F(h->fused.tile_tw);
     wrp::StagedBuffers &b = h->staged;
     F(b.s00), F(b.s01), F(b.s02), F(b.s03), F(b.s04), F(b.s05), F(b.s06), F(b.s07), F(b.s08);
     F(b.rowsum), F(b.power), F(b.result), F(b.ham), F(b.fft_ma), F(b.tw_m), F(b.tw_n_fwd), F(b.tw_n_inv);
-    F(h->x2), F(h->decoded), F(h->power), F(h->ctrl);
+    F(h->x2), F(h->decoded), F(h->power), F(h->ctrl), F(h->stream_scratch), F(h->stream_cnt);
     for (auto &s : h->ring) {
         if (s.pinned_in) cudaFreeHost(s.pinned_in);
         if (s.pinned_out) cudaFreeHost(s.pinned_out);
@@ -147,76 +156,85 @@ static int create_impl(wrp_handle *h)
         CK(h, upload(&h->fused.tw_a, tw_a.data(), tw_a.size() * 4));
         CK(h, upload(&h->fused.tw_b, tw_b.data(), tw_b.size() * 4));
         CK(h, wrp::fused_setup());
-
         const size_t inter = (size_t)C * hmn * sizeof(float2);
-        const char *impl = getenv("WRP_FUSED_IMPL");
-        h->persistent = !(impl && strcmp(impl, "v1") == 0) && wrp::persistent_supported(M, N);
-        if (!h->persistent && !wrp::fused_supported(M, N)) {
-            h->err = "wrp_create: the two-kernel form (WRP_FUSED_IMPL=v1) supports M=1024 only";
+        const bool wire = c.input_fmt == WRP_FMT_WIRE_I16BE;
+        const bool want_fft = c.doppler_form == WRP_DOPPLER_FFT;
+        // kernel family: decided here, once (no environment switches at launch time)
+        if (c.chain_impl == WRP_CHAIN_V1) {
+            if (!wrp::fused_supported(M, N) || want_fft) {
+                h->err = "wrp_create: the two-kernel form (WRP_CHAIN_V1) supports M = 1024 and the literal Doppler transform only via WRP_CHAIN_QUEUE";
+                return WRP_ERR_UNSUPPORTED;
+            }
+            h->chain = wrp_handle::CHAIN_V1;
+        } else if (c.chain_impl == WRP_CHAIN_AUTO && !want_fft && wrp::stream_supported(M, N, 0)) {
+            h->chain = wrp_handle::CHAIN_STREAM;
+        } else if (wrp::persistent_supported(M, N)) {
+            h->chain = wrp_handle::CHAIN_QUEUE;
+        } else {
+            h->err = "wrp_create: no fused kernel for this shape / doppler_form / chain_impl; use WRP_MODE_STAGED";
             return WRP_ERR_UNSUPPORTED;
         }
-        if (h->persistent) {
-            // x2 hand-off = ring of sector slots that stays in L2 (ring * C*(M/2)*N*8 bytes)
+        if (h->chain == wrp_handle::CHAIN_STREAM) {
+            // the streaming kernel decodes wire records on its load path (M = 1024); M = 4096 wire
+            // input goes through the decode pre-pass
+            const int wire_direct = wire && wrp::stream_supported(M, N, 1);
+            h->decode_prepass = wire && !wire_direct;
+            h->smax = 1024;
+            h->chunk = h->smax;
+            CK(h, wrp::stream_setup(M, wire_direct, h->sm_count, &h->stream_max_grid));
+            const int T = M == 4096 ? 4 : 8, NT = N / T;
+            std::vector<float> ttw(4 * (size_t)NT);
+            const double kTwoPi = 6.283185307179586476925286766559;
+            for (int tt = 0; tt < NT; tt++)
+                for (int m = 1; m <= 2; m++) {
+                    const double a = -kTwoPi * (double)(((long long)T * tt * m) % N) / N;
+                    ttw[4 * (size_t)tt + 2 * (m - 1)] = (float)std::cos(a);
+                    ttw[4 * (size_t)tt + 2 * (m - 1) + 1] = (float)std::sin(a);
+                }
+            CK(h, upload(&h->fused.tile_tw, ttw.data(), ttw.size() * 4));
+            for (int m = 1; m <= 2; m++)
+                for (int cc = 0; cc < 8; cc++) {
+                    const double a = -kTwoPi * (double)(cc * m) / N, sg = (cc & 1) ? -1.0 : 1.0;
+                    h->wcol[m - 1][cc] = make_float2((float)(sg * std::cos(a)), (float)(sg * std::sin(a)));
+                }
+            CK(h, cudaMalloc((void **)&h->stream_scratch, wrp::stream_scratch_floats(M, h->stream_max_grid) * sizeof(float)));
+            CK(h, cudaMalloc((void **)&h->stream_cnt, sizeof(int) * (size_t)h->smax * (C + 1)));
+            CK(h, cudaMalloc((void **)&h->power, (size_t)h->smax * C * (M / 2) * sizeof(float)));
+        } else if (h->chain == wrp_handle::CHAIN_QUEUE) {
+            h->decode_prepass = wire;
+            // x2 hand-off = ring of sector slots that stays in L2 (ring * C*(M/2)*N*8 bytes); lag 4 / ring 8
+            // measured best for 1024 x 512
             if (M == 4096) { // 24-48 MiB of hand-off per sector: keep as few sectors in flight as the queue allows
                 h->x2_lag = 1;
                 h->x2_ring = 3;
             }
-            {
-                // unified-item kernel (default shape, wrp_unified.cu): the rows of sector s follow its last
-                // tile by (lag - 1) * 64 C items and a ring slot is reused (ring - lag - 1) * 64 C items
-                // after its last rows, so both margins must cover the ~2 items per CTA between a tile's
-                // start and the publication of its completion.  Measured (sectors/s, 143-sector batches):
-                // 4/8 266k, 5/8 274k, 5/9 280k, 5/10 277k, 6/10 281k, 6/11 275k, 7/11 276k, 6/12 265k
-                // (12 slots = 75 MB no longer fit L2 next to the input stream).
-                if (wrp::chain_uses_unified_kernel(M, N, 0)) {
-                    h->x2_lag = 6;
-                    h->x2_ring = 10;
-                }
-            }
-            if (const char *env = getenv("WRP_RING")) h->x2_ring = atoi(env);
-            if (const char *env = getenv("WRP_LAG")) h->x2_lag = atoi(env);
-            if (h->x2_lag < 1) h->x2_lag = 1;
+            if (c.x2_ring > 0) h->x2_ring = c.x2_ring;
+            if (c.x2_lag > 0) h->x2_lag = c.x2_lag;
             if (h->x2_ring < h->x2_lag + 2) h->x2_ring = h->x2_lag + 2; // a tile may only wait for earlier queue items
             if (h->x2_ring > 64) h->x2_ring = 64;
             h->smax = 1024;
             h->chunk = h->smax;
             CK(h, wrp::persistent_setup());
             CK(h, cudaMalloc((void **)&h->x2, inter * h->x2_ring));
-            if (const char *env = getenv("WRP_L2_PERSIST")) {
-                if (atoi(env) > 0) {
-                    // opt-in: carve persisting L2 out for the ring (a device-wide limit, hence not default)
-                    size_t want = inter * h->x2_ring;
-                    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-                    if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
-                    cudaError_t le = cudaErrorInvalidValue;
-                    if (want > 0) le = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-                    if (le == cudaSuccess) h->l2_window = want;
-                    if (getenv("WRP_DEBUG"))
-                        fprintf(stderr, "[wrp debug] L2 persist: ring %zu B, persistingL2CacheMaxSize %d, "
-                                        "accessPolicyMaxWindowSize %d, window %zu, setLimit: %s\n",
-                                inter * h->x2_ring, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize,
-                                h->l2_window, cudaGetErrorString(le));
-                    cudaGetLastError();
-                }
-            }
             CK(h, cudaMalloc((void **)&h->ctrl, sizeof(int) * wrp::persistent_ctrl_ints(h->smax)));
-            CK(h, cudaMalloc((void **)&h->power, (size_t)c.max_batch * C * (M / 2) * sizeof(float)));
-            if (c.input_fmt == WRP_FMT_WIRE_I16BE) {
-                h->chunk = c.max_batch > 8 ? c.max_batch : 8; // decode scratch bounds the launch size
-                CK(h, cudaMalloc((void **)&h->decoded, (size_t)h->chunk * C * mn * sizeof(float2)));
-            }
         } else {
+            h->decode_prepass = wire;
             // chunk: sectors per kernel pair, sized so the range->Doppler hand-off
             // (C*(M/2)*N*8 bytes per sector) stays resident in L2 between the two kernels
             int chunk = (int)((size_t)h->l2_bytes / 3 / inter);
-            if (const char *env = getenv("WRP_CHUNK")) chunk = atoi(env);
             if (chunk < 1) chunk = 1;
             if (chunk > 4096) chunk = 4096;
             h->chunk = chunk;
             CK(h, cudaMalloc((void **)&h->x2, inter * chunk));
             CK(h, cudaMalloc((void **)&h->power, (size_t)chunk * C * (M / 2) * sizeof(float)));
-            if (c.input_fmt == WRP_FMT_WIRE_I16BE)
-                CK(h, cudaMalloc((void **)&h->decoded, (size_t)chunk * C * mn * sizeof(float2)));
+        }
+        if (h->decode_prepass) {
+            // planar scratch of the decode pre-pass, allocated once: it bounds the launch size, so
+            // wrp_process_device never allocates or synchronises
+            int dchunk = c.max_batch > 8 ? c.max_batch : 8;
+            if (dchunk > h->chunk) dchunk = h->chunk;
+            h->chunk = dchunk;
+            CK(h, cudaMalloc((void **)&h->decoded, (size_t)h->chunk * C * mn * sizeof(float2)));
         }
     } else {
         wrp::StagedBuffers &b = h->staged;
@@ -260,7 +278,9 @@ int wrp_create(const wrp_config *cfg, int device, wrp_handle **out)
     if (c.n_channels < 1 || c.n_channels > 3 || c.n_streams < 1 || c.n_streams > 64 || c.ma_taps < 1 ||
         c.ma_taps > 63 || c.max_batch < 1 || c.max_batch > 4096 ||
         (c.input_fmt != WRP_FMT_C64_PLANAR && c.input_fmt != WRP_FMT_WIRE_I16BE) ||
-        (c.mode != WRP_MODE_FUSED && c.mode != WRP_MODE_STAGED)) {
+        (c.mode != WRP_MODE_FUSED && c.mode != WRP_MODE_STAGED) ||
+        (c.doppler_form != WRP_DOPPLER_ENERGY && c.doppler_form != WRP_DOPPLER_FFT) || c.chain_impl < WRP_CHAIN_AUTO ||
+        c.chain_impl > WRP_CHAIN_V1 || c.x2_lag < 0 || c.x2_ring < 0 || c.x2_lag > 32 || c.x2_ring > 64) {
         g_create_error = "wrp_create: configuration field out of range";
         return WRP_ERR_INVALID;
     }
@@ -270,8 +290,8 @@ int wrp_create(const wrp_config *cfg, int device, wrp_handle **out)
         return WRP_ERR_UNSUPPORTED;
     }
     if (c.mode == WRP_MODE_FUSED && !wrp::fused_supported(c.n_rows_M, c.n_cols_N) &&
-        !wrp::persistent_supported(c.n_rows_M, c.n_cols_N)) {
-        g_create_error = "wrp_create: fused mode supports M=1024 or 4096 with N=512 or 1024; use WRP_MODE_STAGED";
+        !wrp::persistent_supported(c.n_rows_M, c.n_cols_N) && !wrp::stream_supported(c.n_rows_M, c.n_cols_N, 0)) {
+        g_create_error = "wrp_create: fused mode supports M=1024 or 4096 with a power-of-two N in [64, 8192]; use WRP_MODE_STAGED";
         return WRP_ERR_UNSUPPORTED;
     }
     int n_dev = 0;
@@ -318,10 +338,12 @@ int wrp_get_info(const wrp_handle *h, wrp_info *info)
     info->l2_bytes = h->l2_bytes;
     info->input_bytes_per_sector = input_bytes_per_sector(c);
     info->output_floats_per_sector = (size_t)c.n_rows_M;
-    info->intermediate_bytes_per_sector = (size_t)c.n_channels * (c.n_rows_M / 2) * c.n_cols_N * 8;
+    info->intermediate_bytes_per_sector =
+        h->chain == wrp_handle::CHAIN_STREAM ? 0 : (size_t)c.n_channels * (c.n_rows_M / 2) * c.n_cols_N * 8;
     info->chunk_sectors = h->chunk;
-    const int wire = c.input_fmt == WRP_FMT_WIRE_I16BE ? 1 : 0;
-    info->kernels_per_chunk = c.mode == WRP_MODE_FUSED ? (h->persistent ? 1 : 2) + wire : 14 + wire;
+    const int pre = h->decode_prepass ? 1 : 0;
+    info->kernels_per_chunk = c.mode == WRP_MODE_FUSED ? (h->chain == wrp_handle::CHAIN_V1 ? 2 : 1) + pre
+                                                       : 14 + (c.input_fmt == WRP_FMT_WIRE_I16BE ? 1 : 0);
     return WRP_OK;
 }
 
@@ -340,10 +362,21 @@ unsigned long long wrp_launch_count(const wrp_handle *h) { return h ? h->launche
 const char *wrp_chain_kernel_name(const wrp_handle *h)
 {
     if (!h) return "";
-    if (h->cfg.mode != WRP_MODE_FUSED) return "staged cascade";
-    if (!h->persistent) return "range_fft_kernel";
-    const bool unified = wrp::chain_uses_unified_kernel(h->cfg.n_rows_M, h->cfg.n_cols_N, h->l2_window);
-    return unified ? "chain_unified_kernel" : "chain_persistent_kernel";
+    switch (h->chain) {
+    case wrp_handle::CHAIN_STREAM: return wrp::stream_kernel_name();
+    case wrp_handle::CHAIN_QUEUE: return "chain_persistent_kernel";
+    case wrp_handle::CHAIN_V1: return "range_fft_kernel";
+    default: return "staged cascade";
+    }
+}
+
+int wrp_set_stage02_tap(wrp_handle *h, void *dev_x2)
+{
+    if (!h) return WRP_ERR_INVALID;
+    if (h->chain != wrp_handle::CHAIN_STREAM)
+        return fail(h, WRP_ERR_STATE, "wrp_set_stage02_tap: the handle does not run the streaming kernel");
+    h->x2_tap = (float2 *)dev_x2;
+    return WRP_OK;
 }
 
 // ---- profiling ------------------------------------------------------------------------
@@ -420,22 +453,6 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
     const int M = c.n_rows_M, N = c.n_cols_N, C = c.n_channels;
     const size_t in_bytes = input_bytes_per_sector(c);
     const size_t out_floats = (size_t)M; // 2 * M/2
-    if (c.mode == WRP_MODE_FUSED && h->persistent && c.input_fmt == WRP_FMT_WIRE_I16BE && n_sectors > h->chunk &&
-        h->chunk < 64) {
-        // a large HBM-resident wire batch: grow the decode scratch (up to 64 sectors) so that the
-        // persistent kernel gets launches long enough to amortise its ramp-up and tail
-        const int want = n_sectors < 64 ? n_sectors : 64;
-        CK(h, cudaStreamSynchronize(st));
-        CK(h, cudaDeviceSynchronize());
-        float2 *bigger = nullptr;
-        if (cudaMalloc((void **)&bigger, (size_t)want * C * M * N * sizeof(float2)) == cudaSuccess) {
-            cudaFree(h->decoded);
-            h->decoded = bigger;
-            h->chunk = want;
-        } else {
-            cudaGetLastError(); // keep the small scratch
-        }
-    }
     for (int s0 = 0; s0 < n_sectors; s0 += h->chunk) {
         const int S = n_sectors - s0 < h->chunk ? n_sectors - s0 : h->chunk;
         const uint8_t *in = (const uint8_t *)dev_iq + (size_t)s0 * in_bytes;
@@ -448,30 +465,55 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
             }
             h->launches += n;
         } else {
-            const float2 *planar = (const float2 *)in;
-            if (c.input_fmt == WRP_FMT_WIRE_I16BE) {
+            const void *chain_in = in;
+            if (h->decode_prepass) {
                 ProfScope ps(h, st, 0);
                 CK(h, wrp::launch_decode_wire(in, h->decoded, M, N, C, S, st));
                 h->launches++;
-                planar = h->decoded;
+                chain_in = h->decoded;
             }
-            if (h->persistent) {
+            if (h->chain == wrp_handle::CHAIN_STREAM) {
                 ProfScope ps(h, st, 4);
-                CK(h, wrp::launch_persistent(planar, out, nullptr, h->x2, h->x2_ring, h->x2_lag, h->ctrl, h->smax, h->fused, M, N,
-                                             C, S, c.range_res_m, c.calib, h->host.taps_sum, h->sm_count, h->l2_window, st));
+                wrp::StreamParams p{};
+                p.wrc_t = h->fused.wrc_t;
+                p.tw_a = h->fused.tw_a;
+                p.wd = h->fused.wd;
+                p.wr4 = h->fused.wr4;
+                p.tw4 = h->fused.tw4;
+                p.tile_tw = h->fused.tile_tw;
+                p.in = chain_in;
+                p.out = out;
+                p.power = h->power;
+                p.x2_tap = h->x2_tap ? h->x2_tap + (size_t)s0 * C * (M / 2) * N : nullptr;
+                p.scratch = h->stream_scratch;
+                p.plane_cnt = h->stream_cnt;
+                p.sector_cnt = h->stream_cnt + (size_t)S * C;
+                p.S = S;
+                p.C = C;
+                p.N = N;
+                p.range_res = c.range_res_m;
+                p.calib = c.calib;
+                p.taps_sum = h->host.taps_sum;
+                memcpy(p.wcol, h->wcol, sizeof p.wcol);
+                const int wire_direct = c.input_fmt == WRP_FMT_WIRE_I16BE && !h->decode_prepass;
+                CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, st));
                 h->launches++;
-                if (const char *dbg = getenv("WRP_DEBUG")) {
-                    if (atoi(dbg) & 16) {
-                        int na = 0, nb = 0;
-                        cudaStreamSynchronize(st);
-                        wrp::persistent_debug_counters(h->ctrl, &na, &nb);
-                        fprintf(stderr, "[wrp debug] %d sectors: dependency unmet at probe: %d range tiles, %d Doppler blocks\n", S, na, nb);
-                    }
+            } else if (h->chain == wrp_handle::CHAIN_QUEUE) {
+                ProfScope ps(h, st, 4);
+                CK(h, wrp::launch_persistent((const float2 *)chain_in, out, nullptr, h->x2, h->x2_ring, h->x2_lag, h->ctrl,
+                                             h->smax, h->fused, M, N, C, S, c.range_res_m, c.calib, h->host.taps_sum,
+                                             h->sm_count, c.doppler_form == WRP_DOPPLER_FFT, c.evict_first, c.debug, st));
+                h->launches++;
+                if (c.debug & 16) {
+                    int na = 0, nb = 0;
+                    cudaStreamSynchronize(st);
+                    wrp::persistent_debug_counters(h->ctrl, &na, &nb);
+                    fprintf(stderr, "[wrp debug] %d sectors: dependency unmet at probe: %d range tiles, %d Doppler blocks\n", S, na, nb);
                 }
             } else {
                 {
                     ProfScope ps(h, st, 1);
-                    CK(h, wrp::launch_range_fft(planar, h->x2, h->fused, M, N, C, S, st));
+                    CK(h, wrp::launch_range_fft((const float2 *)chain_in, h->x2, h->fused, M, N, C, S, st));
                     h->launches++;
                 }
                 {

@@ -1,6 +1,5 @@
-// wrp_chain_params.h — kernel parameters and control-word layout shared by the persistent chain
-// kernels (wrp_persistent.cu: queue of range tiles and Doppler blocks; wrp_unified.cu: one item =
-// one range tile + eight Doppler rows).
+// wrp_chain_params.h — kernel parameters and control-word layout of the two-kind work-queue kernel
+// (wrp_persistent.cu: queue of range tiles and Doppler blocks).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -28,23 +27,12 @@ struct PersistParams {
     int n1, n2, n3, b3_first; // queue regions (see decode_item)
     int total_items;
     int smax;
-    int evict_first; // stream the input through L2 with an evict-first policy (WRP_EVICT_FIRST=0 turns it off)
-    int discard; // drop consumed ring rows from L2 with discard.global.L2 (WRP_DISCARD=1 turns it on)
-    int debug; // WRP_DEBUG development switches
+    int evict_first; // stream the input through L2 with an evict-first policy (wrp_config.evict_first)
+    int discard; // drop consumed ring rows from L2 with discard.global.L2 (off: measured 2 % slower)
+    int debug; // wrp_config.debug development switches
     int zero;  // always 0 (see opaque_smem_addr)
     float range_res, calib, taps_sum;
 };
 constexpr int CTRL_A = 32;
-
-// Which kernel carries a fused batch of this shape under the current environment switches
-// (WRP_CHAIN=queue, WRP_DOPPLER=fft, WRP_TILE_COLS=4, WRP_DISCARD=1 and an L2 access-policy window
-// all select the two-kind queue of wrp_persistent.cu).  The one place that decides: the launch,
-// the lag / ring defaults and wrp_chain_kernel_name all ask here.
-bool chain_uses_unified_kernel(int M, int N, size_t l2_window_bytes);
-
-// wrp_unified.cu: M = 1024, N = 512 only.  p.tiles_a, p.pair_blocks are ignored (recomputed).
-bool unified_supported(int M, int N);
-cudaError_t unified_setup();
-cudaError_t launch_unified(PersistParams p, int sm_count, cudaStream_t st);
 
 } // namespace wrp

@@ -33,6 +33,7 @@ struct FusedTables {
     float2 *tw_b = nullptr;  // [32][R1b]    exp(+2*pi*i*l*ka/N)    Doppler inter-pass twiddles
     float *wr4 = nullptr;    // M = 4096: wr_c in natural order (radix-4 pre-pass window)
     float2 *tw4 = nullptr;   // M = 4096: [1024] exp(-2*pi*i*r/4096) (pre-pass twiddle)
+    float4 *tile_tw = nullptr; // streaming kernel: [N/T] per-tile factors of the two clipped Doppler bins
 };
 
 struct StagedBuffers {
@@ -75,19 +76,26 @@ struct wrp_handle {
     wrp::FusedTables fused;
     wrp::StagedBuffers staged;
 
-    // range -> Doppler hand-off, [chunk][C][M/2][N] float2, reused chunk after chunk so
-    // it stays L2-resident
+    // which kernel family carries a fused batch (decided once, at wrp_create)
+    enum ChainKind { CHAIN_STREAM, CHAIN_QUEUE, CHAIN_V1, CHAIN_STAGED };
+    ChainKind chain = CHAIN_STAGED;
+    bool decode_prepass = false; // wire input is decoded into `decoded` before the chain kernel
+    // streaming kernel (wrp_stream.cu): no hand-off; partial sums of planes cut by the work partition,
+    // per-plane / per-sector arrival counters, row powers [smax][C][M/2]
+    int stream_max_grid = 0;
+    float *stream_scratch = nullptr;
+    int *stream_cnt = nullptr;
+    float2 wcol[2][8] = {};
+    float2 *x2_tap = nullptr; // wrp_set_stage02_tap (caller-owned)
+    // queue / v1 kernels: range -> Doppler hand-off, [ring or chunk][C][M/2][N] float2, L2-resident
     float2 *x2 = nullptr;
-    float2 *decoded = nullptr; // [chunk][C][M][N] planar scratch for wire input
-    float *power = nullptr;    // [chunk][C][M/2]
-    int chunk = 1;
-    // persistent form: x2 is a ring of `ring` sector slots; ctrl holds the work/dependency counters
-    bool persistent = false;
-    int x2_ring = 8; // sector slots of the x2 hand-off ring (50 MB, L2-resident)
-    int x2_lag = 4;  // Doppler blocks of sector t are queued after the range tiles of sector t + lag
+    float2 *decoded = nullptr; // [chunk][C][M][N] planar scratch for wire input (decode pre-pass)
+    float *power = nullptr;    // [smax or chunk][C][M/2]
+    int chunk = 1;             // sectors per launch
+    int x2_ring = 8; // queue kernel: sector slots of the x2 hand-off ring (50 MB, L2-resident)
+    int x2_lag = 4;  // queue kernel: Doppler blocks of sector t are queued after the range tiles of sector t + lag
     int *ctrl = nullptr;
     int smax = 1024; // sectors per persistent launch
-    size_t l2_window = 0; // bytes of the x2 ring pinned in L2 per launch (0 = off)
 
     cudaStream_t compute_stream = nullptr; // all kernels of the host path run here (owns the scratch)
     std::vector<wrp::RingSlot> ring;
@@ -126,7 +134,8 @@ int persistent_ctrl_ints(int smax);
 cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
                               int *ctrl,
                               int smax, const FusedTables &t, int M, int N, int C, int n_sectors, float range_res,
-                              float calib, float taps_sum, int sm_count, size_t l2_window_bytes, cudaStream_t st);
+                              float calib, float taps_sum, int sm_count, bool doppler_fft, int evict_first, int debug,
+                              cudaStream_t st);
 
 void persistent_debug_counters(const int *ctrl, int *not_ready_a, int *not_ready_b);
 

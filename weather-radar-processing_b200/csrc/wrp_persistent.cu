@@ -1,6 +1,7 @@
 // wrp_persistent.cu — the fused chain as ONE persistent kernel per batch (sm_100a): the two-kind
-// work queue.  Carries N = 1024 and M = 4096; the default 1024 x 512 sector runs on wrp_unified.cu
-// (one item = tile + rows) unless WRP_CHAIN=queue or WRP_DOPPLER=fft select this file.
+// work queue with an L2-resident range -> Doppler hand-off ring.  The product path is the hand-off-free
+// streaming kernel (wrp_stream.cu); this file carries the literal Doppler transform
+// (wrp_config.doppler_form = WRP_DOPPLER_FFT) and stays selectable (chain_impl = WRP_CHAIN_QUEUE).
 //
 // Work items, handed out in queue order by an atomic counter:
 //   A(s, tile)  range tile: T (= 8) adjacent columns x 1024 rows of one (sector, channel) plane.
@@ -33,9 +34,6 @@
 // stores have long drained); Doppler blocks are only loaded once their sector's count is full
 // (ld.relaxed.gpu probe; data is then read with cp.async.cg straight from L2).  An item only waits
 // for items earlier in the queue, and nobody spins while holding unpublished work: no deadlock.
-#include <cstdlib>
-#include <cstring>
-
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
 #include "wrp_ptx.cuh"
@@ -737,28 +735,10 @@ int persistent_ctrl_ints(int smax) { return CTRL_A + 2 * smax; }
 
 static int tile_cols(int M)
 {
-    static int t = 0;
-    if (!t) {
-        const char *env = getenv("WRP_TILE_COLS");
-        t = env && atoi(env) == 4 ? 4 : 8; // 8 columns (64-byte row segments) measured 24 % faster than 4
-    }
+    // 8 columns (64-byte row segments) measured 24 % faster than 4 for M = 1024.
     // 4096 rows: 4 columns = 128 KiB tiles, one 16-warp CTA per SM.  (2 columns = 64 KiB tiles with two
     // 8-warp CTAs per SM was measured 20 % slower: 16-byte row pieces, 10x the bank conflicts.)
-    return M == 4096 ? 4 : t;
-}
-
-static bool env_is(const char *name, const char *value)
-{
-    const char *v = getenv(name);
-    return v && !strcmp(v, value);
-}
-static bool doppler_fft_requested() { return env_is("WRP_DOPPLER", "fft"); }
-static bool discard_requested() { return getenv("WRP_DISCARD") && atoi(getenv("WRP_DISCARD")) != 0; }
-
-bool chain_uses_unified_kernel(int M, int N, size_t l2_window_bytes)
-{
-    return unified_supported(M, N) && tile_cols(M) == 8 && !doppler_fft_requested() && !discard_requested() &&
-           l2_window_bytes == 0 && !env_is("WRP_CHAIN", "queue");
+    return M == 4096 ? 4 : 8;
 }
 
 cudaError_t persistent_setup()
@@ -772,20 +752,20 @@ cudaError_t persistent_setup()
                              Tables<R1B, T, Q>::SMEM);                                                       \
     if (e != cudaSuccess) return e;
     WRP_SET(16, 8, 1)
-    WRP_SET(16, 4, 1)
     WRP_SET(32, 8, 1)
-    WRP_SET(32, 4, 1)
     WRP_SET(16, 4, 4)
     WRP_SET(32, 4, 4)
 #undef WRP_SET
-    return unified_setup();
+    return cudaSuccess;
 }
 
-// One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.
+// One launch for the whole batch.  ctrl must hold CTRL_A + 2*smax ints.  The atomic work queue hands
+// items out in dependency order and a CTA only ever waits for items claimed earlier, so the kernel
+// terminates for any number of resident CTAs (the grid is sized from the occupancy query anyway).
 cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2 *x2_ring, int ring, int lag,
                               int *ctrl, int smax, const FusedTables &t, int M, int N, int C, int n_sectors,
-                              float range_res, float calib, float taps_sum, int sm_count, size_t l2_window_bytes,
-                              cudaStream_t st)
+                              float range_res, float calib, float taps_sum, int sm_count, bool doppler_fft,
+                              int evict_first, int debug, cudaStream_t st)
 {
     if (n_sectors == 0) return cudaSuccess;
     if (!persistent_supported(M, N) || n_sectors > smax || ring < lag + 2) return cudaErrorInvalidValue;
@@ -821,57 +801,31 @@ cudaError_t launch_persistent(const float2 *iq, float *out, float *power, float2
     p.total_items = S * (p.tiles_a + p.blocks_b);
     p.smax = smax;
     // (M = 4096: the hand-off of even one sector exceeds L2, so protecting it buys nothing; measured 5 % slower)
-    p.evict_first = getenv("WRP_EVICT_FIRST") ? atoi(getenv("WRP_EVICT_FIRST")) : (M == 1024);
-    p.discard = discard_requested(); // -2 % throughput; evict-first already keeps the ring in L2
-    p.debug = getenv("WRP_DEBUG") ? atoi(getenv("WRP_DEBUG")) : 0;
-    // Doppler blocks: energy form (default) or the literal two-pass transform (WRP_DOPPLER=fft)
-    const bool doppler_fft = doppler_fft_requested();
+    p.evict_first = evict_first >= 0 ? evict_first : (M == 1024);
+    p.discard = 0;
+    p.debug = debug;
     p.range_res = range_res;
     p.calib = calib;
     p.taps_sum = taps_sum;
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(int) * (CTRL_A + 2 * (size_t)smax), st);
     if (e != cudaSuccess) return e;
-    // Default sector shape: the unified-item kernel (one item = range tile + eight Doppler rows,
-    // wrp_unified.cu).  WRP_CHAIN=queue keeps the two-kind work queue of this file.
-    if (chain_uses_unified_kernel(M, N, l2_window_bytes)) return launch_unified(p, sm_count, st);
     int grid = (16 / NW) * sm_count;
     if (grid > p.total_items) grid = p.total_items;
-
-    // Optional (WRP_L2_PERSIST=1, which also carves persisting L2 out at wrp_create): pin the x2
-    // ring in L2 for this launch through an access-policy window, so the streamed input cannot push
-    // the hand-off rows out to DRAM.
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(32 * NW);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    int n_attr = 0;
-    if (l2_window_bytes > 0) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = (void *)x2_ring;
-        attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        n_attr = 1;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n_attr;
 #define WRP_LAUNCH(R1B, TT, QQ)                                                                              \
     do {                                                                                                     \
-        cfg.dynamicSmemBytes = Tables<R1B, TT, QQ>::SMEM;                                                    \
-        if (doppler_fft) return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ, 0>, p);        \
-        return cudaLaunchKernelEx(&cfg, chain_persistent_kernel<R1B, TT, QQ, 1>, p);                         \
+        if (doppler_fft)                                                                                     \
+            chain_persistent_kernel<R1B, TT, QQ, 0><<<grid, 32 * NW, Tables<R1B, TT, QQ>::SMEM, st>>>(p);   \
+        else                                                                                                 \
+            chain_persistent_kernel<R1B, TT, QQ, 1><<<grid, 32 * NW, Tables<R1B, TT, QQ>::SMEM, st>>>(p);   \
+        return cudaGetLastError();                                                                           \
     } while (0)
     if (Q == 4) {
         if (N == 512) WRP_LAUNCH(16, 4, 4);
         WRP_LAUNCH(32, 4, 4);
     }
-    if (N == 512 && T == 8) WRP_LAUNCH(16, 8, 1);
-    if (N == 512) WRP_LAUNCH(16, 4, 1);
-    if (T == 8) WRP_LAUNCH(32, 8, 1);
-    WRP_LAUNCH(32, 4, 1);
+    if (N == 512) WRP_LAUNCH(16, 8, 1);
+    WRP_LAUNCH(32, 8, 1);
 #undef WRP_LAUNCH
 }
 

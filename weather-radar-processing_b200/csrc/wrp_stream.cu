@@ -1,0 +1,608 @@
+// wrp_stream.cu — the fused chain as ONE persistent kernel with NO range -> Doppler hand-off (sm_100a).
+//
+// Stages 03-08 in energy form need, per range gate k of a (sector, channel) plane, only four sums over
+// the Doppler axis j of the range-FFT output x2[k][j]  (rpv2.cu:93-197 collapsed by Parseval, see
+// DESIGN.md section 4.0):
+//     E   = sum_j |x2[k][j]|^2
+//     Y_0 = sum_j x2[k][j]                                   (the bin the mean removal zeroes)
+//     Y_m = sum_j (-1)^j exp(-2 pi i j m / N) x2[k][j], m = 1, 2   (the two clipped bins N/2 - m)
+//     P[k] = (N E - |Y_0|^2 - |Y_1|^2 - |Y_2|^2) * sum(taps)
+// A range tile (T adjacent columns x M rows) contributes T terms to each sum of each of its M/2
+// surviving rows.  So the tile's epilogue folds its rows straight into seven accumulators per gate and
+// the range-FFT output never leaves the SM: no x2 ring in L2, no second kernel phase, no dependency
+// between CTAs, DRAM traffic = the input, L2 traffic = the input.
+//
+// One CTA walks a contiguous run of tiles of one plane after another, carrying the accumulators of
+// the current plane (registers for M = 1024, shared memory for M = 4096):
+//   load   cp.async of the tile, a whole tile ahead (warp-local regions as in wrp_persistent.cu;
+//          wire input: 4-byte cp.async of the channel's int16 pair out of every 12-byte record into a
+//          separate landing buffer, big-endian decode in the first pass — sector.cpp:52-62 on the load path)
+//   pass 1 window folded into the first butterfly stage (rpv2.cu:86-91), radix-32 in registers,
+//          inter-pass twiddle, in-place exchange through shared memory          (stages 01-02,
+//   pass 2 radix-32, outputs k < M/2 only                                        rpv2.cu:318-333,426-428)
+//   fold   outputs staged warp-locally as [gate][T columns], each lane reads whole rows back and
+//          updates E, Y_0, Y_1, Y_2 of its gates (no shuffles, no CTA barrier)
+//   plane end: P[k] -> power[]; the CTA that completes the second of (hh, vv) writes ZdB/ZDR
+//          (rpv2.cu:199-213).  A plane cut by the work partition is summed by the last CTA to arrive
+//          (partials in scratch, fixed order: results do not depend on arrival order).
+// Nothing in this kernel waits for another CTA: any grid size is correct, co-residency is irrelevant.
+#include "wrp_stream.h"
+
+#include "wrp_fft.cuh"
+#include "wrp_internal.h"
+#include "wrp_ptx.cuh"
+
+namespace wrp {
+namespace stream {
+
+constexpr int R = 32;
+constexpr int WRC_ROW = 32 * 4 + 16; // wr(i)*c transposed [32 b][32 a] floats, rows padded by 16 B
+constexpr int TWA_ROW = 32 * 8 + 16; // range inter-pass twiddles [32 b][32 ka] float2
+
+template <int Q, bool WIRE> struct Cfg {
+    static_assert(Q == 1 || (Q == 4 && !WIRE), "M = 1024 (planar or wire) or M = 4096 (planar)");
+    static constexpr int T = Q == 1 ? 8 : 4;      // columns per tile
+    static constexpr int NW = T * Q;              // warps: one per 8 KiB of the exchange buffer
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int PITCH = T * 8;           // bytes per row of the exchange buffer
+    static constexpr int CPR = PITCH / 16;        // 16-byte chunks per row
+    static constexpr int XBUF = 1024 * Q * PITCH; // exchange buffer; also the landing zone of planar input
+    static constexpr int LAND = WIRE ? 1024 * T * 4 : 0; // wire: (I, Q) int16 pairs of the tile
+    static constexpr int KPW = 32 / T;            // ka values per warp
+    static constexpr int ROWS_PHASE = 8 * KPW;    // gates a warp stages per fold phase (8 kb x KPW ka)
+    // planar M = 1024: a separate staging buffer, because the warp's region of the exchange buffer is
+    // already receiving the next tile; wire / M = 4096: the region itself (see the kernel)
+    static constexpr bool STAGE_SEPARATE = Q == 1 && !WIRE;
+    static constexpr int STAGE = STAGE_SEPARATE ? NW * ROWS_PHASE * PITCH : 0;
+    static constexpr int RPT = 2 * ROWS_PHASE / 32; // gates per thread: 2 (M = 1024) or 4 (M = 4096)
+    static constexpr bool ACC_SMEM = Q == 4;
+    static constexpr int ACC = ACC_SMEM ? RPT * 2 * THREADS * 16 : 0; // [gate slot][chunk][thread] float4
+    static constexpr int OFF_LAND = XBUF;
+    static constexpr int OFF_STAGE = OFF_LAND + LAND;
+    static constexpr int OFF_ACC = OFF_STAGE + STAGE;
+    static constexpr int OFF_TAB = OFF_ACC + ACC;
+    static constexpr int OFF_WRC = OFF_TAB;                      // Q = 1
+    static constexpr int OFF_W4 = OFF_TAB;                       // Q = 4: wr(i)*c [4096]
+    static constexpr int OFF_TW4 = OFF_W4 + 4096 * 4;            //        exp(-2 pi i r / 4096) [1024]
+    static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + 32 * WRC_ROW : OFF_TW4 + 1024 * 8;
+    static constexpr int SMEM = OFF_TWA + 32 * TWA_ROW;
+    static_assert((Q == 1 ? 2 : 1) * (SMEM + 1024 + 64) <= 233472, "shared memory per SM");
+};
+
+// ---- tile loads ------------------------------------------------------------------------------
+// planar: the executing warp fetches its own 8 KiB region of the tile (rows [8192/PITCH * warp, ...)),
+// 16 cp.async of 16 B per lane
+template <int Q, bool WIRE>
+__device__ __forceinline__ void issue_tile_planar(const StreamParams &p, uint8_t *xbuf, uint64_t *bar, int plane, int t,
+                                                  int warp, int lane)
+{
+    using K = Cfg<Q, WIRE>;
+    constexpr int RPWARP = 8192 / K::PITCH;
+    const size_t row_bytes = (size_t)p.N * 8;
+    const uint8_t *src = (const uint8_t *)p.in + ((size_t)plane * (1024 * Q) + warp * RPWARP + lane / K::CPR) * row_bytes +
+                         (size_t)t * K::PITCH + (lane % K::CPR) * 16;
+    uint8_t *dst = xbuf + warp * 8192 + lane * 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / K::CPR) * row_bytes);
+    cp_async_arrive(bar);
+}
+// wire: every thread fetches 32 of the tile's 8192 (I, Q) pairs — 4 bytes at offset 4 ch of the
+// 12-byte record (sector.cpp:52-62) — into the dense landing buffer [row][8 columns]
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void issue_tile_wire(const StreamParams &p, uint8_t *land, uint64_t *bar, int sector, int ch,
+                                                int t, int tid)
+{
+    const size_t row_bytes = (size_t)p.N * 12;
+    const int row = tid >> 3, c = tid & 7;
+    const uint8_t *src =
+        (const uint8_t *)p.in + ((size_t)sector * 1024 + row) * row_bytes + ((size_t)t * 8 + c) * 12 + ch * 4;
+    uint8_t *dst = land + tid * 4;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) cp_async4(dst + k * 1024, src + (size_t)k * 32 * row_bytes);
+    cp_async_arrive(bar);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+template <int Q, bool WIRE>
+__global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1) chain_stream_kernel(const StreamParams p)
+{
+    using K = Cfg<Q, WIRE>;
+    constexpr int T = K::T, NW = K::NW, THREADS = K::THREADS, PITCH = K::PITCH, CPR = K::CPR, KPW = K::KPW;
+    constexpr int RPT = K::RPT;
+    constexpr int SW = 128 / PITCH - 1; // row-swizzle mask of the in-place exchange
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar; // the next tile has landed: one arrival per thread, fired by its cp.asyncs
+    __shared__ __align__(8) uint64_t ebar; // wire: every warp is done with its staged rows of the previous tile
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *const xbuf = smem;
+
+    // ---- work partition: a contiguous run of tiles of the [virtual plane][tile] space --------------
+    const int CG = p.chan_groups;
+    const int grp = blockIdx.x % CG, u = blockIdx.x / CG, Gp = gridDim.x / CG;
+    if (u >= Gp) return;
+    const long long total = (long long)(CG == 1 ? p.S * p.C : p.S) * p.NT;
+    const int g_lo = (int)((long long)u * total / Gp), g_end = (int)(((long long)u + 1) * total / Gp);
+    if (g_lo >= g_end) return;
+    auto real_plane = [&](int vp) { return CG == 1 ? vp : vp * p.C + grp; };
+    auto cta_of = [&](long long g) { return (int)(((g + 1) * Gp - 1) / total); }; // u of the CTA that owns tile g
+
+    // ---- tables -> shared memory -----------------------------------------------------------------
+    {
+        auto copy_rows = [&](int off, const void *src, int rows, int row_bytes, int row_pitch) {
+            const int per_row = row_bytes / 16;
+            for (int i = tid; i < rows * per_row; i += THREADS) {
+                const int r = i / per_row, q = i - r * per_row;
+                *reinterpret_cast<float4 *>(smem + off + r * row_pitch + q * 16) =
+                    __ldg(reinterpret_cast<const float4 *>(src) + i);
+            }
+        };
+        if constexpr (Q == 1) {
+            copy_rows(K::OFF_WRC, p.wrc_t, 32, 32 * 4, WRC_ROW);
+        } else {
+            copy_rows(K::OFF_W4, p.wr4, 1, 4096 * 4, 4096 * 4);
+            copy_rows(K::OFF_TW4, p.tw4, 1, 1024 * 8, 1024 * 8);
+        }
+        copy_rows(K::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
+        if constexpr (K::ACC_SMEM) {
+            for (int i = tid; i < K::ACC / 16; i += THREADS)
+                *reinterpret_cast<float4 *>(smem + K::OFF_ACC + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&mbar, THREADS);
+        mbar_init(&ebar, NW);
+    }
+    __syncthreads();
+
+    int vp = g_lo / p.NT, t = g_lo - vp * p.NT; // virtual plane and tile of the current item
+    const int vp_lo = vp;
+    auto issue_tile = [&](int vplane, int tile) {
+        const int plane = real_plane(vplane);
+        if constexpr (WIRE) {
+            const int sector = plane / p.C;
+            issue_tile_wire(p, smem + K::OFF_LAND, &mbar, sector, plane - sector * p.C, tile, tid);
+        } else {
+            issue_tile_planar<Q, WIRE>(p, xbuf, &mbar, plane, tile, warp, lane);
+        }
+    };
+    issue_tile(vp, t);
+
+    // ---- per-thread constants of the fold ---------------------------------------------------------
+    // writer: thread (column c, ka_l) stores output kb of the phase at staged row R = kbl * KPW + ka_l;
+    // 16-byte chunk (c >> 1) of a row is XOR-swizzled with s(R) so that the 128-bit row reads below are
+    // conflict-free: s(R) = (R >> 1) & 3 for 64-byte rows, (R >> 2) & 1 for 32-byte rows
+    const int cw = lane % T, ka_l = lane / T;
+    uint8_t *const stage = K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH) : xbuf + warp * 8192;
+    uint8_t *wbase[2]; // by parity of kbl (T = 8: s depends on it; T = 4: both entries equal)
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+        const int s = T == 8 ? ((par << 1) | (ka_l >> 1)) : ((ka_l >> 2) & 1);
+        wbase[par] = stage + ka_l * PITCH + (((cw >> 1) ^ s) << 4) + (cw & 1) * 8;
+    }
+    // reader: lane reads staged rows R = lane (+ 32 for 32-byte rows); logical chunk q sits at q ^ s(R)
+    const int rs = T == 8 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+    const uint8_t *const rbase = stage + lane * PITCH;
+    // gate of fold slot r of this thread (r = phase for M = 1024; r = 2 phase + i for M = 4096)
+    auto slot_gate = [&](int r) {
+        if constexpr (Q == 1) {
+            const int kb = 8 * r + (lane >> 2), ka = 4 * warp + (lane & 3);
+            return ka + 32 * kb;
+        } else {
+            const int h = r >> 1, i = r & 1;
+            const int kb = 8 * h + (lane >> 3) + 4 * i, ka = 8 * (warp & 3) + (lane & 7);
+            return 4 * (ka + 32 * kb) + (warp >> 2);
+        }
+    };
+    float acc[K::ACC_SMEM ? 1 : RPT][7]; // E, Re/Im Y_0, Re/Im Y_1, Re/Im Y_2 (registers, M = 1024)
+    if constexpr (!K::ACC_SMEM) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[r][q] = 0.f;
+    }
+    float4 *const acc_s = reinterpret_cast<float4 *>(smem + K::OFF_ACC) + tid; // [slot][chunk][thread]
+
+    uint32_t phase = 0, ephase = 0;
+    bool first = true;
+
+    for (int g = g_lo; g < g_end; ++g) {
+        int nt = t + 1, nvp = vp;
+        if (nt == p.NT) nt = 0, ++nvp;
+        const bool has_next = g + 1 < g_end;
+        const int plane = real_plane(vp);
+        const float4 ttw = __ldg(p.tile_tw + t); // this tile's factors of the two clipped bins
+
+        // thread -> (sub-tile, column, b): Q = 4: thread group `sub` (32 T threads) owns the 1024-row sub-tile k0 = sub
+        const int sub = Q == 1 ? 0 : tid / (32 * T), tl = Q == 1 ? tid : tid % (32 * T);
+        const int c = tl % T, b = tl / T;
+        const int col0 = t * T, col = col0 + c;
+        uint8_t *const stile = xbuf + sub * (1024 * PITCH);
+        float wdj = 0.f;
+        float2 wdp = make_float2(0.f, 0.f);
+        if constexpr (Q == 1) wdj = __ldg(p.wd + col);
+        else wdp = __ldg(reinterpret_cast<const float2 *>(p.wd + col0) + tid % (T / 2));
+
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+
+        if constexpr (Q == 4) {
+            // stage 01 + radix-4 DIF step over rows r, r + 1024, r + 2048, r + 3072, in place:
+            //   y_k0[r] = W_4096^(r k0) * sum_q (-i)^(q k0) ham(r + 1024 q) x[r + 1024 q]
+            // one unit = one row r x two adjacent columns (16-byte accesses); the 1024-point transforms of
+            // the four sub-tiles then yield rows 4 k' + k0 of the 4096-point transform
+            constexpr int UNITS = 1024 * T / 2;
+            const int cp = tid % (T / 2);
+            const float *wr4 = reinterpret_cast<const float *>(smem + K::OFF_W4);
+            const float2 *tw4 = reinterpret_cast<const float2 *>(smem + K::OFF_TW4);
+#pragma unroll 2
+            for (int un = tid; un < UNITS; un += THREADS) {
+                const int r = un / (T / 2);
+                uint8_t *ptr = xbuf + r * PITCH + cp * 16;
+                float4 x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = *reinterpret_cast<const float4 *>(ptr + q * (1024 * PITCH));
+                float2 e[4], o[4]; // even / odd column of the pair
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float w = wr4[r + 1024 * q];
+                    const float wa = w * wdp.x, wb = w * wdp.y;
+                    e[q] = cmul2(make_float2(x[q].x, x[q].y), make_float2(wa, wa));
+                    o[q] = cmul2(make_float2(x[q].z, x[q].w), make_float2(wb, wb));
+                }
+                const float2 w1 = tw4[r], w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                auto radix4 = [&](float2(&z)[4]) {
+                    const float2 t0 = cadd(z[0], z[2]), t1 = csub(z[0], z[2]);
+                    const float2 t2 = cadd(z[1], z[3]), d = csub(z[1], z[3]);
+                    const float2 t3 = make_float2(d.y, -d.x); // -i (x1 - x3)
+                    z[0] = cadd(t0, t2);
+                    z[1] = cmul(cadd(t1, t3), w1);
+                    z[2] = cmul(csub(t0, t2), w2);
+                    z[3] = cmul(csub(t1, t3), w3);
+                };
+                radix4(e);
+                radix4(o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4 *>(ptr + q * (1024 * PITCH)) = make_float4(e[q].x, e[q].y, o[q].x, o[q].y);
+            }
+            __syncthreads();
+        }
+
+        // ================= pass 1: rows 32 a + b of column c =================
+        float2 v[R];
+        if constexpr (WIRE) {
+            // big-endian int16 (I, Q) -> float: one PRMT per component swaps the bytes and extends the sign
+            const uint8_t *src = smem + K::OFF_LAND + b * (T * 4) + c * 4;
+            static_for<R>([&](auto ai) {
+                constexpr int a = decltype(ai)::value;
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(src + a * (R * T * 4));
+                v[brev<R>(a)] = make_float2((float)(int)__byte_perm(w, 0u, 0x8801), (float)(int)__byte_perm(w, 0u, 0xAA23));
+            });
+        } else {
+            const uint8_t *src = stile + b * PITCH + c * 8;
+            static_for<R>([&](auto ai) {
+                constexpr int a = decltype(ai)::value;
+                v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
+            });
+        }
+        if constexpr (Q == 1) {
+            // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage: the span-1
+            // partners of the bit-reversed network are rows a and a + 16
+            const float2 m2 = make_float2(-2.f, -2.f);
+            const float4 *w4 = reinterpret_cast<const float4 *>(smem + K::OFF_WRC + b * WRC_ROW);
+            static_for<R / 8>([&](auto qi) { // rows 4q .. 4q+3 and their partners 16 + 4q ..
+                constexpr int q = decltype(qi)::value;
+                const float4 wlo = w4[q], whi = w4[q + R / 8];
+                const float lo[4] = {wlo.x, wlo.y, wlo.z, wlo.w}, hi[4] = {whi.x, whi.y, whi.z, whi.w};
+                static_for<4>([&](auto ei) {
+                    constexpr int e = decltype(ei)::value;
+                    constexpr int sa = brev<R>(4 * q + e); // even slot; partner row a + R/2 sits in sa + 1
+                    static_assert(brev<R>(4 * q + e + R / 2) == sa + 1, "span-1 partner");
+                    const float wl = lo[e] * wdj, wh = hi[e] * wdj;
+                    const float2 tt = cmul2(v[sa + 1], make_float2(wh, wh));
+                    const float2 s2 = cfma2(v[sa], make_float2(wl, wl), tt); // A*wl + B*wh
+                    v[sa + 1] = cfma2(tt, m2, s2);                            // A*wl - B*wh
+                    v[sa] = s2;
+                });
+            });
+            fft_dit_after_stage1<R, -1>(v);
+        } else {
+            fft_dit<R, -1>(v);
+        }
+        if constexpr (WIRE) {
+            // the exchange buffer doubles as the fold's staging area: wait until every warp has read its
+            // staged rows of the previous tile back before overwriting them
+            if (!first) {
+                mbar_wait(&ebar, ephase);
+                ephase ^= 1;
+            }
+        }
+        {
+            // Z[ka][b] goes to row 32 ka + (b ^ (ka & SW)): the warp keeps its own row footprint (in place);
+            // the twiddle reads run two steps ahead of the exchange stores
+            const float4 *t4 = reinterpret_cast<const float4 *>(smem + K::OFF_TWA + b * TWA_ROW);
+            uint8_t *d_sw[SW + 1];
+#pragma unroll
+            for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = stile + (b ^ sx) * PITCH + c * 8;
+            float4 wq[3] = {t4[0], t4[1], t4[2]};
+            static_for<R / 2>([&](auto qi) {
+                constexpr int q = decltype(qi)::value;
+                const float4 w = wq[q % 3];
+                if constexpr (q + 3 < R / 2) wq[q % 3] = t4[q + 3];
+                const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
+                *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
+            });
+        }
+        // the exchange: the one barrier of a 1024-point column group
+        if constexpr (Q == 1) {
+            __syncthreads();
+        } else { // constant barrier ids, so that only 5 of the 16 are reserved
+            if (sub == 0) bar_sync_id<2>(32 * T);
+            else if (sub == 1) bar_sync_id<3>(32 * T);
+            else if (sub == 2) bar_sync_id<4>(32 * T);
+            else bar_sync_id<5>(32 * T);
+        }
+        if constexpr (WIRE) {
+            if (has_next) issue_tile(nvp, nt); // the landing buffer is free: every thread is past its first pass
+        }
+
+        // ================= pass 2: rows 32 ka + b' of column c, ka = b =================
+        const int ka = b; // rows 32 ka + .. of warp w are its own 8 KiB region
+        {
+            const uint8_t *s_sw[SW + 1];
+#pragma unroll
+            for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = stile + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
+            static_for<R>([&](auto bi) {
+                constexpr int bb = decltype(bi)::value;
+                v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(s_sw[bb & SW] + (bb & ~SW) * PITCH);
+            });
+        }
+        __syncwarp();
+        if constexpr (K::STAGE_SEPARATE) {
+            if (has_next) issue_tile(nvp, nt); // the warp's region is in registers: fetch its share of the next tile
+        }
+        fft_dit<R, -1>(v);
+        if (p.x2_tap) { // debug tap (tests): stage 02 rows k < M/2 as the product kernel computes them
+            float2 *o = p.x2_tap + ((size_t)plane * p.half_m + Q * ka + sub) * (size_t)p.N + col;
+            static_for<R / 2>([&](auto ki) {
+                constexpr int kb = decltype(ki)::value;
+                o[(size_t)(Q * R * kb) * p.N] = v[kb];
+            });
+        }
+
+        // ================= fold: stages 03-08 in energy form =================
+        // output kb of (c, ka) is gate Q (ka + 32 kb) + sub, column col.  Two phases of eight kb: stage the
+        // warp's outputs as rows [gate][T columns], read whole rows back, update the gate's seven sums.
+        static_for<2>([&](auto hi_) {
+            constexpr int h = decltype(hi_)::value;
+            static_for<8>([&](auto ki) {
+                constexpr int kbl = decltype(ki)::value;
+                *reinterpret_cast<float2 *>(wbase[kbl & 1] + kbl * (KPW * PITCH)) = v[8 * h + kbl];
+            });
+            __syncwarp();
+            static_for<RPT / 2>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                constexpr int slot = (RPT / 2) * h + i;
+                float2 x[T];
+                static_for<CPR>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = *reinterpret_cast<const float4 *>(rbase + i * (32 * PITCH) + ((q ^ rs) << 4));
+                    x[2 * q] = make_float2(w.x, w.y);
+                    x[2 * q + 1] = make_float2(w.z, w.w);
+                });
+                float2 e2 = cmul2(x[0], x[0]);
+                float2 s0 = x[0], s1 = x[0], s2 = x[0];
+                static_for<T - 1>([&](auto ci) {
+                    constexpr int cc = decltype(ci)::value + 1;
+                    e2 = cfma2(x[cc], x[cc], e2);
+                    s0 = cadd(s0, x[cc]);
+                    const float2 w1 = p.wcol[0][cc], w2 = p.wcol[1][cc];
+                    s1.x = fmaf(x[cc].x, w1.x, s1.x);
+                    s1.x = fmaf(-x[cc].y, w1.y, s1.x);
+                    s1.y = fmaf(x[cc].x, w1.y, s1.y);
+                    s1.y = fmaf(x[cc].y, w1.x, s1.y);
+                    s2.x = fmaf(x[cc].x, w2.x, s2.x);
+                    s2.x = fmaf(-x[cc].y, w2.y, s2.x);
+                    s2.y = fmaf(x[cc].x, w2.y, s2.y);
+                    s2.y = fmaf(x[cc].y, w2.x, s2.y);
+                });
+                float a7[7];
+                if constexpr (K::ACC_SMEM) {
+                    const float4 lo = acc_s[(slot * 2 + 0) * THREADS], hi4 = acc_s[(slot * 2 + 1) * THREADS];
+                    a7[0] = lo.x, a7[1] = lo.y, a7[2] = lo.z, a7[3] = lo.w, a7[4] = hi4.x, a7[5] = hi4.y, a7[6] = hi4.z;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) a7[q] = acc[slot][q];
+                }
+                a7[0] += e2.x + e2.y;
+                a7[1] += s0.x;
+                a7[2] += s0.y;
+                a7[3] = fmaf(s1.x, ttw.x, a7[3]);
+                a7[3] = fmaf(-s1.y, ttw.y, a7[3]);
+                a7[4] = fmaf(s1.x, ttw.y, a7[4]);
+                a7[4] = fmaf(s1.y, ttw.x, a7[4]);
+                a7[5] = fmaf(s2.x, ttw.z, a7[5]);
+                a7[5] = fmaf(-s2.y, ttw.w, a7[5]);
+                a7[6] = fmaf(s2.x, ttw.w, a7[6]);
+                a7[6] = fmaf(s2.y, ttw.z, a7[6]);
+                if constexpr (K::ACC_SMEM) {
+                    acc_s[(slot * 2 + 0) * THREADS] = make_float4(a7[0], a7[1], a7[2], a7[3]);
+                    acc_s[(slot * 2 + 1) * THREADS] = make_float4(a7[4], a7[5], a7[6], 0.f);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) acc[slot][q] = a7[q];
+                }
+            });
+            __syncwarp();
+        });
+        if constexpr (WIRE) {
+            if (lane == 0) mbar_arrive(&ebar);
+        }
+        if constexpr (!K::STAGE_SEPARATE && !WIRE) {
+            if (has_next) issue_tile(nvp, nt); // staged rows consumed: the region may receive the next tile
+        }
+
+        // ================= end of the plane (or of this CTA's run): products =================
+        if (nt == 0 || !has_next) {
+            const int hm = p.half_m;
+            const long long plane_first = (long long)vp * p.NT;
+            const bool complete = g_lo <= plane_first && nt == 0;
+            float vals[RPT][7];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                if constexpr (K::ACC_SMEM) {
+                    const float4 lo = acc_s[(r * 2 + 0) * THREADS], hi4 = acc_s[(r * 2 + 1) * THREADS];
+                    vals[r][0] = lo.x, vals[r][1] = lo.y, vals[r][2] = lo.z, vals[r][3] = lo.w;
+                    vals[r][4] = hi4.x, vals[r][5] = hi4.y, vals[r][6] = hi4.z;
+                    acc_s[(r * 2 + 0) * THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc_s[(r * 2 + 1) * THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) {
+                        vals[r][q] = acc[r][q];
+                        acc[r][q] = 0.f;
+                    }
+                }
+            }
+            bool finalize = complete;
+            if (!complete) {
+                // the plane is shared with neighbouring CTAs: park the partial sums, the last to arrive adds
+                // the parts in CTA order.  Slot 0 = the plane this CTA's run starts in, slot 1 = any other.
+                float *mine = p.scratch + ((size_t)blockIdx.x * 2 + (vp == vp_lo ? 0 : 1)) * 7 * hm;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int k = slot_gate(r);
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) mine[q * hm + k] = vals[r][q];
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) s_flag = atomicAdd(p.plane_cnt + plane, 1);
+                __syncthreads();
+                const int x_first = cta_of(plane_first), x_last = cta_of(plane_first + p.NT - 1);
+                if (s_flag == x_last - x_first) {
+                    __threadfence();
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) vals[r][q] = 0.f;
+                    for (int x = x_first; x <= x_last; ++x) {
+                        const int x_vp_lo = (int)(((long long)x * total / Gp) / p.NT);
+                        const float *part =
+                            p.scratch + ((size_t)(x * CG + grp) * 2 + (vp == x_vp_lo ? 0 : 1)) * 7 * hm;
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            const int k = slot_gate(r);
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) vals[r][q] += __ldcg(part + q * hm + k);
+                        }
+                    }
+                    finalize = true;
+                }
+            }
+            if (finalize) {
+                const int sector = plane / p.C, ch = plane - sector * p.C;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int k = slot_gate(r);
+                    float removed = vals[r][1] * vals[r][1];
+#pragma unroll
+                    for (int q = 2; q < 7; ++q) removed = fmaf(vals[r][q], vals[r][q], removed);
+                    // stages 05-08: the row sum of the circular convolution is sum(taps) x the row sum
+                    const float pw = fmaxf(fmaf(p.n_float, vals[r][0], -removed), 0.f) * p.taps_sum;
+                    p.power[(size_t)plane * hm + k] = pw;
+                    if (p.C == 1) { // stage 09 only (rpv2.cu:199-213 with a single channel)
+                        const float rg = (float)k * p.range_res;
+                        reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
+                            make_float2(10.f * log10f(rg * rg * p.calib * pw), 0.f);
+                    }
+                }
+                if (p.C >= 2 && ch < 2) {
+                    // stages 09/10 need hh and vv of the gate: whoever finishes the second of the two planes
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) s_flag = atomicAdd(p.sector_cnt + sector, 1);
+                    __syncthreads();
+                    if (s_flag == 1) {
+                        __threadfence();
+                        const float *ph = p.power + (size_t)sector * p.C * hm, *pv = ph + hm;
+                        for (int k = tid; k < hm; k += THREADS) {
+                            const float hh = __ldcg(ph + k), vv = __ldcg(pv + k);
+                            const float rg = (float)k * p.range_res;
+                            reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
+                                make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv)));
+                        }
+                    }
+                }
+            }
+        }
+        first = false;
+        t = nt;
+        vp = nvp;
+    }
+}
+
+} // namespace stream
+
+// ---- host side ---------------------------------------------------------------------------------
+bool stream_supported(int M, int N, int wire)
+{
+    if (N < 64 || N > 8192 || (N & (N - 1))) return false;
+    if (M == 1024) return true;
+    return M == 4096 && !wire;
+}
+
+const char *stream_kernel_name() { return "chain_stream_kernel"; }
+
+template <int Q, bool WIRE> static cudaError_t setup_one(int sm_count, int *max_grid)
+{
+    using K = stream::Cfg<Q, WIRE>;
+    cudaError_t e = cudaFuncSetAttribute(stream::chain_stream_kernel<Q, WIRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream::chain_stream_kernel<Q, WIRE>, K::THREADS, K::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *max_grid = per_sm * sm_count;
+    return cudaSuccess;
+}
+
+cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid)
+{
+    if (M == 4096) return setup_one<4, false>(sm_count, max_grid);
+    return wire ? setup_one<1, true>(sm_count, max_grid) : setup_one<1, false>(sm_count, max_grid);
+}
+
+size_t stream_scratch_floats(int M, int max_grid) { return (size_t)max_grid * 2 * 7 * (M / 2); }
+
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, cudaStream_t st)
+{
+    if (p.S <= 0) return cudaSuccess;
+    const int T = M == 4096 ? 4 : 8;
+    p.NT = p.N / T;
+    p.half_m = M / 2;
+    p.n_float = (float)p.N;
+    p.chan_groups = (wire || channel_groups) ? p.C : 1;
+    const long long total = (long long)(p.chan_groups == 1 ? p.S * p.C : p.S) * p.NT;
+    long long grid = max_grid / p.chan_groups;
+    if (grid > total) grid = total;
+    grid *= p.chan_groups;
+    cudaError_t e = cudaMemsetAsync(p.plane_cnt, 0, sizeof(int) * (size_t)p.S * (p.C + 1), st); // plane_cnt + sector_cnt
+    if (e != cudaSuccess) return e;
+    if (M == 4096)
+        stream::chain_stream_kernel<4, false><<<(int)grid, stream::Cfg<4, false>::THREADS, stream::Cfg<4, false>::SMEM, st>>>(p);
+    else if (wire)
+        stream::chain_stream_kernel<1, true><<<(int)grid, stream::Cfg<1, true>::THREADS, stream::Cfg<1, true>::SMEM, st>>>(p);
+    else
+        stream::chain_stream_kernel<1, false><<<(int)grid, stream::Cfg<1, false>::THREADS, stream::Cfg<1, false>::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace wrp

@@ -1,0 +1,46 @@
+// wrp_stream.h — parameters and host entry points of the streaming chain kernel (wrp_stream.cu):
+// the fused chain WITHOUT a range -> Doppler hand-off.  Not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wrp {
+
+struct FusedTables;
+
+struct StreamParams {
+    // tables (device)
+    const float *wrc_t;     // [32 b][32 a] wr(32 a + b) * c          (M = 1024: window of the first butterfly stage)
+    const float2 *tw_a;     // [32 b][32 ka] exp(-2 pi i b ka / 1024)  (inter-pass twiddles of the 32 x 32 transform)
+    const float *wd;        // [N] Doppler window wd(j)
+    const float *wr4;       // M = 4096: wr(i) * c, natural order
+    const float2 *tw4;      // M = 4096: exp(-2 pi i r / 4096), r < 1024 (radix-4 pre-pass)
+    const float4 *tile_tw;  // [N / T] (cos, sin) of -2 pi T t m / N for m = 1 and m = 2: a tile's factor of the clipped bins
+    // data
+    const void *in;         // planar [S][C][M][N] float2, or wire records [S][M][N] x 12 B
+    float *out;             // [S][M/2][2]  (ZdB, ZDR)
+    float *power;           // [S][C][M/2]  row powers (also the hh/vv exchange between the CTAs that finish the planes)
+    float2 *x2_tap;         // optional debug tap: range-FFT rows k < M/2, [S][C][M/2][N]; NULL in production
+    float *scratch;         // [grid][2][7][M/2] partial sums of planes shared between CTAs
+    int *plane_cnt;         // [S * C] parts of a shared plane that have arrived
+    int *sector_cnt;        // [S] finished (hh, vv) planes of a sector
+    int S, C, N, NT;        // sectors, channels, Doppler length, tiles per plane (N / T)
+    int half_m;             // M / 2
+    int chan_groups;        // 1: CTAs split the [plane][tile] space; C: CTA x works on channel x % C of the
+                            // [sector][tile] space, so the C CTAs that read the same wire records run side by side
+    float n_float, range_res, calib, taps_sum;
+    float2 wcol[2][8];      // (-1)^c exp(-2 pi i c m / N), m = 1, 2: column c's factor of clipped bin N/2 - m inside a tile
+};
+
+bool stream_supported(int M, int N, int wire);
+// occupancy-derived grid (CTAs that are certainly co-resident are not required: no CTA ever waits for another)
+cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid);
+size_t stream_scratch_floats(int M, int max_grid);
+// channel_groups != 0 forces the wire path's work partition (CTA x -> channel x % C) on planar input too,
+// so that both formats associate their sums identically (bit-exactness tests of the decode)
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, cudaStream_t st);
+const char *stream_kernel_name();
+
+} // namespace wrp
