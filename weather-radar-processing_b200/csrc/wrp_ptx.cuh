@@ -127,6 +127,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// byte permute with PTX semantics: selector nibble n = byte index 0-7 of {b, a}; bit 3 of a nibble
+// replicates that byte's sign bit instead (the __byte_perm intrinsic masks bit 3 away)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // cp.async groups: the calling thread's copies since its previous commit form one group
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait_group()

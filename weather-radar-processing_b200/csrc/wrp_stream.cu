@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1) chain_s
             static_for<R>([&](auto ai) {
                 constexpr int a = decltype(ai)::value;
                 const uint32_t w = *reinterpret_cast<const uint32_t *>(src + a * (R * T * 4));
-                v[brev<R>(a)] = make_float2((float)(int)__byte_perm(w, 0u, 0x8801), (float)(int)__byte_perm(w, 0u, 0xAA23));
+                // memory bytes I_hi I_lo Q_hi Q_lo = bytes 0..3 of w: I = sext(b0 : b1), Q = sext(b2 : b3)
+                v[brev<R>(a)] = make_float2((float)(int)prmt(w, 0u, 0x8801u), (float)(int)prmt(w, 0u, 0xAA23u));
             });
         } else {
             const uint8_t *src = stile + b * PITCH + c * 8;
