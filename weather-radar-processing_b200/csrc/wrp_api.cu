@@ -182,6 +182,11 @@ static int create_impl(wrp_handle *h)
             h->smax = 1024;
             h->chunk = h->smax;
             CK(h, wrp::stream_setup(M, wire_direct, h->sm_count, &h->stream_max_grid));
+            if (!wire_direct) { // planar tiles are fetched by TMA: the tensor map of a launch is encoded on the host
+                cudaDriverEntryPointQueryResult q;
+                CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->tma_encode, cudaEnableDefault, &q));
+                if (!h->tma_encode) return fail(h, WRP_ERR_CUDA, "wrp_create: the driver does not export cuTensorMapEncodeTiled");
+            }
             const int T = M == 4096 ? 4 : 8, NT = N / T;
             std::vector<float> ttw(4 * (size_t)NT);
             const double kTwoPi = 6.283185307179586476925286766559;
@@ -496,7 +501,10 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 p.taps_sum = h->host.taps_sum;
                 memcpy(p.wcol, h->wcol, sizeof p.wcol);
                 const int wire_direct = c.input_fmt == WRP_FMT_WIRE_I16BE && !h->decode_prepass;
-                CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, st));
+                CUtensorMap tmap{};
+                if (!wire_direct && !wrp::stream_encode_tensor_map(h->tma_encode, &tmap, chain_in, M, N, (long long)S * C))
+                    return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the batch (is the device buffer 16-byte aligned?)");
+                CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, tmap, st));
                 h->launches++;
             } else if (h->chain == wrp_handle::CHAIN_QUEUE) {
                 ProfScope ps(h, st, 4);

@@ -14,8 +14,9 @@
 //
 // One CTA walks a contiguous run of tiles of one plane after another, carrying the accumulators of
 // the current plane (registers for M = 1024, shared memory for M = 4096):
-//   load   cp.async of the tile, a whole tile ahead (warp-local regions as in wrp_persistent.cu;
-//          wire input: 4-byte cp.async of the channel's int16 pair out of every 12-byte record into a
+//   load   the tile, a whole tile ahead: planar input by TMA (cp.async.bulk.tensor, one 8 KiB box per
+//          warp-local region of the tile buffer, issued the moment the warp has pulled its last operand
+//          out of it); wire input: 4-byte cp.async of the channel's int16 pair out of every 12-byte record into a
 //          separate landing buffer, big-endian decode in the first pass — sector.cpp:52-62 on the load path)
 //   pass 1 window folded into the first butterfly stage (rpv2.cu:86-91), radix-32 in registers,
 //          inter-pass twiddle, in-place exchange through shared memory          (stages 01-02,
@@ -70,21 +71,32 @@ template <int Q, bool WIRE> struct Cfg {
 };
 
 // ---- tile loads ------------------------------------------------------------------------------
-// planar: the executing warp fetches its own 8 KiB region of the tile (rows [8192/PITCH * warp, ...)),
-// 16 cp.async of 16 B per lane
+// planar: TMA.  The warp's own 8 KiB region of the tile (rows [8192/PITCH * warp, ...)) is one box
+// {T columns x 8192/PITCH rows} of the batch viewed as a [planes * M][N] matrix of 8-byte elements:
+// lane 0 posts the byte count on the tile barrier and issues one cp.async.bulk.tensor — no LDGSTS, no
+// per-lane address arithmetic, and the shared-memory write side does not go through the LSU
+// (tools/micro/tile_load.cu: 64-byte-row boxes sustain the same 6.8 TB/s as cp.async).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 template <int Q, bool WIRE>
-__device__ __forceinline__ void issue_tile_planar(const StreamParams &p, uint8_t *xbuf, uint64_t *bar, int plane, int t,
+__device__ __forceinline__ void issue_tile_planar(const CUtensorMap *tmap, uint8_t *xbuf, uint64_t *bar, int plane, int t,
                                                   int warp, int lane)
 {
     using K = Cfg<Q, WIRE>;
     constexpr int RPWARP = 8192 / K::PITCH;
-    const size_t row_bytes = (size_t)p.N * 8;
-    const uint8_t *src = (const uint8_t *)p.in + ((size_t)plane * (1024 * Q) + warp * RPWARP + lane / K::CPR) * row_bytes +
-                         (size_t)t * K::PITCH + (lane % K::CPR) * 16;
-    uint8_t *dst = xbuf + warp * 8192 + lane * 16;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) cp_async16(dst + k * 512, src + (size_t)k * (32 / K::CPR) * row_bytes);
-    cp_async_arrive(bar);
+    if (lane == 0) {
+        mbar_expect_tx(bar, 8192);
+        tma_load_2d(xbuf + warp * 8192, tmap, t * K::T, plane * (1024 * Q) + warp * RPWARP, bar);
+    }
 }
 // wire: every thread fetches 32 of the tile's 8192 (I, Q) pairs — 4 bytes at offset 4 ch of the
 // 12-byte record (sector.cpp:52-62) — into the dense landing buffer [row][8 columns]
@@ -107,14 +119,16 @@ __device__ __forceinline__ void issue_tile_wire(const StreamParams &p, uint8_t *
 
 // ---- the kernel ------------------------------------------------------------------------------
 template <int Q, bool WIRE>
-__global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1) chain_stream_kernel(const StreamParams p)
+__global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
+    chain_stream_kernel(const StreamParams p, const __grid_constant__ CUtensorMap tmap)
 {
     using K = Cfg<Q, WIRE>;
     constexpr int T = K::T, NW = K::NW, THREADS = K::THREADS, PITCH = K::PITCH, CPR = K::CPR, KPW = K::KPW;
     constexpr int RPT = K::RPT;
     constexpr int SW = 128 / PITCH - 1; // row-swizzle mask of the in-place exchange
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar; // the next tile has landed: one arrival per thread, fired by its cp.asyncs
+    __shared__ __align__(8) uint64_t mbar; // the next tile has landed: planar — one arrival + 8 KiB of TMA bytes per warp;
+                                           // wire — one arrival per thread, fired by its cp.asyncs
     __shared__ __align__(8) uint64_t ebar; // wire: every warp is done with its staged rows of the previous tile
     __shared__ int s_flag;
 
@@ -154,7 +168,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1) chain_s
         }
     }
     if (tid == 0) {
-        mbar_init(&mbar, THREADS);
+        mbar_init(&mbar, WIRE ? THREADS : NW);
         mbar_init(&ebar, NW);
     }
     __syncthreads();
@@ -167,7 +181,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1) chain_s
             const int sector = plane / p.C;
             issue_tile_wire(p, smem + K::OFF_LAND, &mbar, sector, plane - sector * p.C, tile, tid);
         } else {
-            issue_tile_planar<Q, WIRE>(p, xbuf, &mbar, plane, tile, warp, lane);
+            issue_tile_planar<Q, WIRE>(&tmap, xbuf, &mbar, plane, tile, warp, lane);
         }
     };
     issue_tile(vp, t);
@@ -583,7 +597,25 @@ cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid)
 
 size_t stream_scratch_floats(int M, int max_grid) { return (size_t)max_grid * 2 * 7 * (M / 2); }
 
-cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, cudaStream_t st)
+bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    if (!encode_fn) return false;
+    const int T = M == 4096 ? 4 : 8;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)planes * M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)T, (cuuint32_t)(8192 / (8 * T))};
+    const cuuint32_t estr[2] = {1, 1};
+    // complex floats travel as opaque 8-byte elements
+    return ((EncodeFn)encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, const CUtensorMap &tmap,
+                          cudaStream_t st)
 {
     if (p.S <= 0) return cudaSuccess;
     const int T = M == 4096 ? 4 : 8;
@@ -598,11 +630,11 @@ cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int cha
     cudaError_t e = cudaMemsetAsync(p.plane_cnt, 0, sizeof(int) * (size_t)p.S * (p.C + 1), st); // plane_cnt + sector_cnt
     if (e != cudaSuccess) return e;
     if (M == 4096)
-        stream::chain_stream_kernel<4, false><<<(int)grid, stream::Cfg<4, false>::THREADS, stream::Cfg<4, false>::SMEM, st>>>(p);
+        stream::chain_stream_kernel<4, false><<<(int)grid, stream::Cfg<4, false>::THREADS, stream::Cfg<4, false>::SMEM, st>>>(p, tmap);
     else if (wire)
-        stream::chain_stream_kernel<1, true><<<(int)grid, stream::Cfg<1, true>::THREADS, stream::Cfg<1, true>::SMEM, st>>>(p);
+        stream::chain_stream_kernel<1, true><<<(int)grid, stream::Cfg<1, true>::THREADS, stream::Cfg<1, true>::SMEM, st>>>(p, tmap);
     else
-        stream::chain_stream_kernel<1, false><<<(int)grid, stream::Cfg<1, false>::THREADS, stream::Cfg<1, false>::SMEM, st>>>(p);
+        stream::chain_stream_kernel<1, false><<<(int)grid, stream::Cfg<1, false>::THREADS, stream::Cfg<1, false>::SMEM, st>>>(p, tmap);
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // the fused chain WITHOUT a range -> Doppler hand-off.  Not part of the C ABI.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -40,7 +41,13 @@ cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid);
 size_t stream_scratch_floats(int M, int max_grid);
 // channel_groups != 0 forces the wire path's work partition (CTA x -> channel x % C) on planar input too,
 // so that both formats associate their sums identically (bit-exactness tests of the decode)
-cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, cudaStream_t st);
+// tmap: planar input only — 2-D tensor map over the batch viewed as [S*C*M rows][N] 8-byte elements with
+// box {T columns, 8192 / (8 T) rows} (stream_encode_tensor_map); wire input passes a zeroed map
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, const CUtensorMap &tmap,
+                          cudaStream_t st);
+// Encodes the tensor map of one launch (host-side, no CUDA call besides the driver's encoder).
+// encode_fn = cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (libwrp does not link libcuda).
+bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes);
 const char *stream_kernel_name();
 
 } // namespace wrp
