@@ -9,7 +9,7 @@ CXX      := g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -std=c++17 -O3 -lineinfo -Xcompiler -fPIC
 LIB      := $(PKG)/libwrp.so
-OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_stream.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o
+OBJS     := $(CSRC)/wrp_fused.o $(CSRC)/wrp_persistent.o $(CSRC)/wrp_stream.o $(CSRC)/wrp_staged.o $(CSRC)/wrp_api.o $(CSRC)/wrp_tables.o $(CSRC)/wrp_volume.o
 
 HOSTLIB  := $(PKG)/libwrphost.so
 HOSTSRC  := $(HOST)/dimension.cpp $(HOST)/sector.cpp $(HOST)/floats.c $(HOST)/radar_processor.cpp $(HOST)/stage_dump.cpp
@@ -32,6 +32,9 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/wrp_internal.h $(CSRC)/wrp_fft.cuh $(CSRC)/wrp
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(CSRC)/wrp_tables.o: $(CSRC)/wrp_tables.cpp $(CSRC)/wrp_internal.h include/wrp.h
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+$(CSRC)/wrp_volume.o: $(CSRC)/wrp_volume.cpp include/wrp.h
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
 $(LIB): $(OBJS)

@@ -9,12 +9,18 @@ default sector shape 1024 x 512 x 3 (rpv2.cu:38-45), ``--sectors`` sectors per G
 ours:
   value      whole-job sectors/s with the batch already resident in HBM as planar complex
              float — the reference's own device format (rpv2.cu:379-381) — through
-             wrp_process_device (CUDA events on the launching stream, max over ranks).
+             wrp_process_device (CUDA events on the launching stream, max over ranks).  A burst
+             figure (K steps of 0.4 ms); `sustained` repeats the same step back to back for
+             >= 2.5 s with the clocks and the power sampled meanwhile.
   e2e        the same metric through the public host-buffer call wrp_process_host with
              pinned HOST buffers in the radar's wire format (what the reference's
              read_matrix receives, sector.cpp:52-62): H2D of every step's input and D2H of
              its products are inside the timed region.
-  roofline   dominant kernel (range FFT) against the measured HBM copy bandwidth in
+  volume     BASELINE config 4 at this N: one volume scan (9 x 143 wire sectors in pinned host
+             memory) sharded contiguously over the ranks, products gathered — strong scaling.
+  stress     BASELINE config 5 at this N: 4096 x 1024 x 3 sectors, 64 resident per GPU, against
+             the HBM roofline — weak scaling.
+  roofline   dominant kernel (chain_stream_kernel) against the measured HBM copy bandwidth in
              MEASURED_PEAKS.json: algorithmic bytes per launch / mean launch time (CUDA events
              recorded around every launch inside the timed region).
   cpu_baseline  the oracle's float chain (CPU port of read_single.cc) on all host cores,
@@ -25,8 +31,9 @@ reference:
   on all host cores; rank 0 only.
 
 Multi-GPU (torchrun, one rank per GPU): sectors are independent, each rank
-processes its own shard — weak scaling — and the product volume is all-gathered over NCCL
-inside the step; there is no other collective.
+processes its own shard — weak scaling — and every step's products are all-gathered over NCCL on a
+side stream, overlapped with the next step's kernel (the timed region ends after the last gather);
+there is no other collective.
 """
 from __future__ import annotations
 
@@ -51,6 +58,8 @@ ALGO_BYTES_C64 = C * M * N * 8 + (M // 2) * 8      # 12 587 008
 ALGO_BYTES_WIRE = M * N * 12 + (M // 2) * 8        # 6 295 552
 WORKLOAD = ("default sector 1024x512x3 (rpv2.cu:38-45), all stages fused; one step = one 360-degree PPI "
             "elevation of 143 sectors (rpv2.cu:39 n_sectors) per GPU")
+# the SAME object in both arms' `config` (the driver compares them); run details go under `run`
+CONFIG = {"workload": WORKLOAD, "M": M, "N": N, "channels": C, "sectors_per_elevation": 143}
 
 
 def load_peaks():
@@ -96,7 +105,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, pw, reasons = [], [], [], set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
@@ -104,6 +113,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 smax.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
@@ -112,7 +122,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 def cpu_baseline_port(sample_sectors: int, target_seconds: float = 12.0):
@@ -185,13 +195,115 @@ def run_reference(args):
         "impl": "reference", "metric": "sectors_per_s", "value": v, "unit": "sectors/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sectors_per_step": done // steps, "input_fmt": "wire_i16be",
-                   "M": M, "N": N, "channels": C},
+        "config": dict(CONFIG),
+        "run": {"sectors_per_step": done // steps, "input_fmt": "wire_i16be",
+                "note": "the reference's own CPU chain (read_single.cc) on the host cores; FFTW is absent from the image, "
+                        "the stand-in is oracle/shim/fftw3.h — a CPU baseline, NOT the reference's cuFFT cascade"},
         "cpu_baseline": {"value": v, "unit": "sectors/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "sectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _dist_env():
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def _max_over_ranks(x, dev, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _timed_launches(fn, n, stream):
+    """n back-to-back calls of fn() on `stream`, device time in ms (CUDA events)."""
+    import torch
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(n):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
+def leg_volume(wrp, args, dev, world, rank, local_rank, steps):
+    """BASELINE config 4 at this N: one volume scan = 9 elevations x 143 sectors of wire records in pinned
+    host memory, contiguous (elevation, sector) shards (rpv2.cu:572-579 order), products gathered on the
+    device (one all-gather) — strong scaling.  Returns the JSON object (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    synth = wrp.synth
+    S, E = 143, 9
+    U = S * E
+    lo, hi = wrp.volume.shard_bounds(U, rank, world)
+    base = [synth.to_wire(synth.make_sector_int16(M, N, s, 0)) for s in range(4)]
+    pin = wrp.PinnedBuffer((hi - lo) * M * N * 12)
+    view = pin.array.reshape(hi - lo, M * N * 12)
+    for k in range(lo, hi):
+        view[k - lo] = base[k % 4].reshape(-1)
+    chain = wrp.RadarChain(local_rank, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=args.host_piece, n_streams=args.streams)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    vol = wrp.volume.process_volume(chain, pin, U, dev)  # warm-up: pinned ring, NCCL channels
+    barrier()
+    l0 = chain.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vol = wrp.volume.process_volume(chain, pin, U, dev)
+    barrier()
+    dt = _max_over_ranks(time.perf_counter() - t0, dev, world)
+    v = vol.cpu().numpy()
+    # the gathered volume is checked: shape, finite, and unit k equals unit k mod 4 (same synthetic sector)
+    ok = v.shape == (U, M // 2, 2) and np.isfinite(v[:, 1:]).all() and all(
+        np.allclose(v[k, 1:], v[k % 4, 1:], rtol=0, atol=1e-3) for k in range(0, U, 61))
+    launches = chain.launch_count - l0
+    chain.close()
+    pin.close()
+    if not ok:
+        raise SystemExit("bench.py: gathered volume is wrong")
+    value = U * steps / dt
+    return {"value": value, "unit": "sectors/s", "scaling": "strong", "ms_per_volume": dt / steps * 1e3,
+            "units": U, "steps": steps, "volume_bytes": int(v.nbytes), "gathered_volume_checked": True,
+            "h2d_gbs_per_gpu": value / world * M * N * 12 / 1e9, "gpu_launches": int(launches),
+            "note": "9 elevations x 143 wire sectors from pinned host memory, contiguous (elevation, sector) shards, "
+                    "products stay on the device and are all-gathered once per volume"}
+
+
+def leg_stress(wrp, args, dev, world, local_rank, stream, peak):
+    """BASELINE config 5 at this N: 4096 x 1024 x 3 planar sectors, `--stress-sectors` resident per GPU."""
+    import torch
+    synth = wrp.synth
+    SM_, SN_, SS_ = 4096, 1024, args.stress_sectors
+    sx = synth.to_planar(synth.make_sector_int16(SM_, SN_, 0, 0), C)
+    d_sx = torch.from_numpy(np.ascontiguousarray(sx).view(np.float32).reshape(-1)).to(dev).repeat(SS_)
+    d_so = torch.empty((SS_, SM_ // 2, 2), dtype=torch.float32, device=dev)
+    reps = 5
+    with wrp.RadarChain(local_rank, n_rows_M=SM_, n_cols_N=SN_, n_channels=C, max_batch=1) as sch:
+        kernel = sch.chain_kernel
+        run = lambda: sch.process_device(d_sx.data_ptr(), SS_, d_so.data_ptr(), stream.cuda_stream)
+        for _ in range(2):
+            run()
+        ms = _max_over_ranks(_timed_launches(run, reps, stream), dev, world)
+    if not torch.isfinite(d_so[:, 1:]).all():
+        raise SystemExit("bench.py: non-finite stress products")
+    sv = world * SS_ * reps / (ms * 1e-3)
+    sbytes = C * SM_ * SN_ * 8 + (SM_ // 2) * 2 * 4
+    del d_sx, d_so
+    return {"value": sv, "unit": "sectors/s", "scaling": "weak", "shape": f"{SM_}x{SN_}x{C} c64",
+            "sectors_resident_per_gpu": SS_, "kernel": kernel, "algorithmic_bytes_per_sector": sbytes,
+            "gbs_per_gpu": sv / world * sbytes / 1e9, "hbm_frac": sv / world * sbytes / 1e9 / peak}
 
 
 def run_ours(args):
@@ -200,9 +312,7 @@ def run_ours(args):
 
     wrp = importlib.import_module("weather-radar-processing_b200")
     synth = wrp.synth
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local_rank = _dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -212,20 +322,36 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     S = args.sectors
     steps, warmup = args.steps, args.warmup
+    peak, peak_src = load_peaks()
 
     # ---- inputs: a few distinct synthetic sectors tiled to the batch; larger than L2 --------
     planar = synth.make_batch(M, N, S, fmt="planar", first_sector=rank * 7, distinct=4)
     d_in = torch.from_numpy(planar.view(np.float32).reshape(-1)).to(dev)
-    d_out = torch.empty((S, M // 2, 2), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * S, M // 2, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    d_out = [torch.empty((S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+    gathered = [torch.empty((world * S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
     chain = wrp.RadarChain(local_rank, max_batch=args.host_piece)
     info = chain.info
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_done = [None, None]
+    step_no = [0]
 
     def step():
-        chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
+        """One PPI elevation per GPU; its products are all-gathered on the side stream while the next
+        step's kernel already runs (double-buffered outputs)."""
+        i = step_no[0] & 1
+        step_no[0] += 1
+        if world > 1 and gather_done[i] is not None:
+            stream.wait_event(gather_done[i])  # the gather that read this output buffer two steps ago
+        chain.process_device(d_in.data_ptr(), S, d_out[i].data_ptr(), stream.cuda_stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, d_out)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered[i], d_out[i])
+                gather_done[i] = torch.cuda.Event()
+                gather_done[i].record(side)
 
     def barrier():
         if world > 1:
@@ -245,54 +371,51 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(steps):
         step()
+    if world > 1:
+        stream.wait_stream(side)  # the timed region ends after the last gather
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = chain.launch_count - l0
     chain.profile_enable(False)
     prof = chain.profile_read(reset=True)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = _max_over_ranks(ms, dev, world)
     value = world * S * steps / (ms * 1e-3)
-
     chain_kernel = chain.chain_kernel
+    if world > 1:  # the gathered volume of the last step holds every rank's products
+        g = gathered[(step_no[0] - 1) & 1]
+        own = d_out[(step_no[0] - 1) & 1]
+        if not torch.equal(g[rank * S:(rank + 1) * S], own) or not torch.isfinite(g[:, 1:]).all():
+            raise SystemExit("bench.py: all-gathered products are wrong")
 
-    # ---- side figures: the other forms of the same chain on the same resident batch -----------
-    # (environment switches read by libwrp at create/launch time; each gets its own handle)
+    # ---- sustained leg: the same step back to back for >= 2.5 s, clocks and power sampled meanwhile ----
+    run = lambda: chain.process_device(d_in.data_ptr(), S, d_out[0].data_ptr(), stream.cuda_stream)
+    n_sus = max(int(args.sustain_seconds / (ms / steps * 1e-3)), steps)
+    sus_sampler = ClockSampler(local_rank)
+    sus_sampler.start()
+    time.sleep(0.25)
+    ms_sus = _max_over_ranks(_timed_launches(run, n_sus, stream), dev, world)
+    time.sleep(0.15)
+    sus_clocks = sus_sampler.stop()
+    sustained = {"value": world * S * n_sus / (ms_sus * 1e-3), "unit": "sectors/s", "seconds": ms_sus * 1e-3,
+                 "launches": n_sus, "hbm_frac": S * n_sus / (ms_sus * 1e-3) * ALGO_BYTES_C64 / 1e9 / peak,
+                 "clocks": sus_clocks}
+
+    # ---- side figures: the other forms of the same chain on the same resident batch (N = 1 only) ----
     alt = {}
     if world == 1:
-        for name, env in (("two_kind_queue_energy_form", {"WRP_CHAIN": "queue"}),
-                          ("two_kind_queue_doppler_fft", {"WRP_DOPPLER": "fft"})):
-            saved = {k: os.environ.get(k) for k in env}
-            os.environ.update(env)
-            try:
-                with wrp.RadarChain(local_rank, max_batch=args.host_piece) as alt_chain:
-                    for _ in range(3):
-                        alt_chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
-                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    torch.cuda.synchronize()
-                    a0.record(stream)
-                    for _ in range(steps):
-                        alt_chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
-                    a1.record(stream)
-                    torch.cuda.synchronize()
-                    v = S * steps / (a0.elapsed_time(a1) * 1e-3)
-                    alt[name] = {"value": v, "unit": "sectors/s", "kernel": alt_chain.chain_kernel, "env": env,
-                                 "hbm_frac": v * ALGO_BYTES_C64 / 1e9 / load_peaks()[0]}
-            finally:
-                for k, v0 in saved.items():
-                    if v0 is None:
-                        os.environ.pop(k, None)
-                    else:
-                        os.environ[k] = v0
-        # leave the default form's products in d_out for the checks below
-        chain.process_device(d_in.data_ptr(), S, d_out.data_ptr(), stream.cuda_stream)
-        torch.cuda.synchronize()
-
-    # sanity: products finite beyond gate 0
-    host = d_out.cpu().numpy()
+        for name, cfg in (("two_kind_queue_energy_form", {"chain_impl": wrp.CHAIN_QUEUE}),
+                          ("two_kind_queue_doppler_fft", {"doppler_form": wrp.DOPPLER_FFT})):
+            with wrp.RadarChain(local_rank, max_batch=args.host_piece, **cfg) as alt_chain:
+                f = lambda: alt_chain.process_device(d_in.data_ptr(), S, d_out[1].data_ptr(), stream.cuda_stream)
+                for _ in range(3):
+                    f()
+                v = S * steps / (_timed_launches(f, steps, stream) * 1e-3)
+                alt[name] = {"value": v, "unit": "sectors/s", "kernel": alt_chain.chain_kernel, "config": cfg,
+                             "hbm_frac": v * ALGO_BYTES_C64 / 1e9 / peak}
+    run()
+    torch.cuda.synchronize()
+    host = d_out[0].cpu().numpy()
     if not np.isfinite(host[:, 1:, :]).all():
         raise SystemExit("bench.py: non-finite products")
 
@@ -312,74 +435,51 @@ def run_ours(args):
     for _ in range(steps):
         wire_chain.process_host(pin_in, S2, out_e2e)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt = _max_over_ranks(time.perf_counter() - t0, dev, world)
     launches_e2e = wire_chain.launch_count - l1
-    if world > 1:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
     e2e_value = world * S2 * steps / dt
 
-    # ---- side figure: the same batch resident in HBM in the wire format (int16 ingest, SURVEY §8d) ----
-    d_wire = torch.from_numpy(wire_np.reshape(-1)).to(dev)
-    d_out2 = torch.empty((S2, M // 2, 2), dtype=torch.float32, device=dev)
-    for _ in range(3):
-        wire_chain.process_device(d_wire.data_ptr(), S2, d_out2.data_ptr(), stream.cuda_stream)
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    w0.record(stream)
-    for _ in range(steps):
-        wire_chain.process_device(d_wire.data_ptr(), S2, d_out2.data_ptr(), stream.cuda_stream)
-    w1.record(stream)
-    torch.cuda.synchronize()
-    wire_resident = S2 * steps / (w0.elapsed_time(w1) * 1e-3)
-    clocks = sampler.stop()
-    del d_wire, d_out2
+    # ---- the ceiling of that leg: plain cudaMemcpyAsync of the same pinned bytes, all ranks at once ----
+    d_wire = torch.empty(wire_np.nbytes, dtype=torch.uint8, device=dev)
+    h_wire = torch.from_numpy(pin_in.array)  # a view of the pinned buffer
+    copy = lambda: d_wire.copy_(h_wire, non_blocking=True)
+    copy()
+    barrier()
+    ms_copy = _max_over_ranks(_timed_launches(copy, 5, stream), dev, world) / 5
+    h2d_ceiling_gbs = wire_np.nbytes / (ms_copy * 1e-3) / 1e9  # per GPU, with every rank copying
 
-    # ---- side figure: the stress shape (BASELINE config 5: M = 4096, N = 1024, 64 sectors resident per GPU) ----
-    stress = None
-    if args.stress_sectors > 0:
-        SM_, SN_, SS_ = 4096, 1024, args.stress_sectors
-        sx = synth.to_planar(synth.make_sector_int16(SM_, SN_, 0, 0), C)
-        d_sx = torch.from_numpy(np.ascontiguousarray(sx).view(np.float32).reshape(-1)).to(dev).repeat(SS_)
-        d_so = torch.empty((SS_, SM_ // 2, 2), dtype=torch.float32, device=dev)
-        with wrp.RadarChain(local_rank, n_rows_M=SM_, n_cols_N=SN_, n_channels=C, max_batch=1) as sch:
-            for _ in range(2):
-                sch.process_device(d_sx.data_ptr(), SS_, d_so.data_ptr(), stream.cuda_stream)
-            torch.cuda.synchronize()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            for _ in range(5):
-                sch.process_device(d_sx.data_ptr(), SS_, d_so.data_ptr(), stream.cuda_stream)
-            s1.record(stream)
-            torch.cuda.synchronize()
-        sv = SS_ * 5 / (s0.elapsed_time(s1) * 1e-3)
-        sbytes = C * SM_ * SN_ * 8 + (SM_ // 2) * 2 * 4
-        stress = {"value": sv, "unit": "sectors/s per GPU", "shape": f"{SM_}x{SN_}x{C} c64", "sectors_resident": SS_,
-                  "algorithmic_bytes_per_sector": sbytes, "gbs": sv * sbytes / 1e9}
-        del d_sx, d_so
+    # ---- side figure: the same batch resident in HBM in the wire format (int16 ingest, SURVEY §8d) ----
+    d_out2 = torch.empty((S2, M // 2, 2), dtype=torch.float32, device=dev)
+    fw = lambda: wire_chain.process_device(d_wire.data_ptr(), S2, d_out2.data_ptr(), stream.cuda_stream)
+    for _ in range(3):
+        fw()
+    wire_resident = S2 * steps / (_timed_launches(fw, steps, stream) * 1e-3)
+    clocks = sampler.stop()
+    wire_kernels = wire_chain.info.kernels_per_chunk
+    del d_wire, d_out2
+    wire_chain.close()
 
     # cross-check: the wire path and the planar path see the same sectors -> same products
     n_chk = min(S, S2, 4)
     if not np.allclose(out_e2e[:n_chk, 1:], host[:n_chk, 1:], rtol=0, atol=1e-3):
         raise SystemExit("bench.py: e2e (wire) and HBM-resident (planar) products disagree")
+    pin_in.close()
+
+    # ---- BASELINE config 5 (stress shape) and config 4 (volume scan) at this N ----
+    stress = leg_stress(wrp, args, dev, world, local_rank, stream, peak) if args.stress_sectors > 0 else None
+    volume = leg_volume(wrp, args, dev, world, rank, local_rank, args.volume_steps) if args.volume_steps > 0 else None
 
     if rank == 0:
-        peak, peak_src = load_peaks()
-        if int(prof.n_chain) > 0:
-            kernel, n_k, ms_k = chain_kernel, int(prof.n_chain), prof.ms_chain
-        else:
-            kernel, n_k, ms_k = "range_fft_kernel", max(int(prof.n_range), 1), prof.ms_range
+        n_k, ms_k = max(int(prof.n_chain), 1), prof.ms_chain
         sectors_per_launch = S * steps / n_k
-        range_ms = ms_k / n_k
-        achieved = sectors_per_launch * ALGO_BYTES_C64 / (range_ms * 1e-3) / 1e9
+        launch_ms = ms_k / n_k
+        achieved = sectors_per_launch * ALGO_BYTES_C64 / (launch_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "latest_summary.json")) as f:
-                traffic = json.load(f).get(kernel + "_dram_bytes_per_launch")
+                traffic = json.load(f).get(chain_kernel + "_dram_bytes_per_launch")
         except Exception:
             pass
-        chain_gbs = value / world * ALGO_BYTES_C64 / 1e9
         # reported on rank 0 at N = 1 only (torchrun also pins OMP_NUM_THREADS=1 on its workers)
         cpu = None
         if world == 1:
@@ -389,28 +489,34 @@ def run_ours(args):
             "metric": "sectors_per_s", "value": value, "unit": "sectors/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sectors_per_step_per_gpu": S, "input_fmt": "c64_planar",
-                       "M": M, "N": N, "channels": C, "chunk_sectors": int(info.chunk_sectors),
-                       "l2": f"input batch {d_in.numel() * 4 / 1e6:.0f} MB per GPU > L2 {info.l2_bytes / 1e6:.0f} MB, no flush needed",
-                       "parallelism": f"sectors sharded over {world} GPU(s), products all-gathered"},
+            "config": dict(CONFIG),
+            "run": {"sectors_per_step_per_gpu": S, "input_fmt": "c64_planar", "chunk_sectors": int(info.chunk_sectors),
+                    "l2": f"input batch {d_in.numel() * 4 / 1e6:.0f} MB per GPU > L2 {info.l2_bytes / 1e6:.0f} MB, no flush needed",
+                    "parallelism": f"sectors sharded over {world} GPU(s); every step's products all-gathered on a side "
+                                   "stream, overlapped with the next step's kernel"},
             "iq_gbs": value * ALGO_BYTES_C64 / 1e9,
+            "chain_hbm_frac": value / world * ALGO_BYTES_C64 / 1e9 / peak,
+            "sustained": sustained,
             "wire_resident": {"value": wire_resident, "unit": "sectors/s per GPU", "input_fmt": "wire_i16be",
-                              "hbm_frac": wire_resident * ALGO_BYTES_WIRE / 1e9 / peak,
-                              "note": "HBM-resident int16 wire sectors: decode pre-pass + chain kernel per chunk of up to 64 sectors"},
-            "chain_hbm_frac": chain_gbs / peak,
+                              "hbm_frac": wire_resident * ALGO_BYTES_WIRE / 1e9 / peak, "kernels_per_launch": int(wire_kernels),
+                              "note": "HBM-resident int16 wire sectors, decoded on the streaming kernel's load path (no decode pre-pass)"},
             "chain_forms": {"default": {"kernel": chain_kernel,
-                                        "note": "one item = range tile + eight Doppler rows; stages 03-08 in energy "
-                                                "form (Parseval: row energy minus the DC and the two clipped bins)"},
+                                        "note": "streaming kernel: range tiles folded into per-gate sums, no range->Doppler "
+                                                "hand-off; stages 03-08 in energy form (Parseval)"},
                             **alt},
-            "stress_4096x1024": None if stress is None else dict(stress, hbm_frac=stress["gbs"] / peak),
-            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
+            "stress": stress,
+            "volume": volume,
+            "roofline": {"bound": "hbm", "kernel": chain_kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": sectors_per_launch * ALGO_BYTES_C64,
-                         "mean_launch_ms": range_ms,
-                         "kernel_share_of_step": ms_k / ms},
+                         "mean_launch_ms": launch_ms, "kernel_share_of_step": ms_k / ms,
+                         "traffic_source": "profiles/latest_summary.json (ncu --set full of this command, dram__bytes_read+write per launch)"},
             "e2e": {"value": e2e_value, "unit": "sectors/s", "h2d_bytes_per_step": S2 * M * N * 12,
                     "d2h_bytes_per_step": S2 * M * 4, "input_fmt": "wire_i16be", "sectors_per_step_per_gpu": S2,
                     "h2d_gbs": e2e_value / world * M * N * 12 / 1e9, "api": "wrp_process_host",
+                    "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                    "frac_of_h2d_ceiling": (e2e_value / world * M * N * 12 / 1e9) / h2d_ceiling_gbs,
+                    "h2d_ceiling_note": "plain cudaMemcpyAsync of the same pinned buffer, every rank copying at once, per GPU",
                     "host_cores_bound_per_rank": len(numa_cores)},
             "gpu_launches": int(launches + launches_e2e),
             "clocks": clocks,
@@ -422,70 +528,28 @@ def run_ours(args):
 
 
 def run_volume(args):
-    """BASELINE config 4: one volume scan = 9 elevations x 143 sectors = 1287 wire-format
-    sectors in pinned host memory, sharded contiguously over the ranks, product volume gathered.
-    Strong scaling; one step = one volume.  Not the default bench line (that is config 2/3)."""
+    """`--workload volume`: only the config-4 leg, as its own JSON line (strong scaling)."""
     import torch
     import torch.distributed as dist
 
     wrp = importlib.import_module("weather-radar-processing_b200")
-    synth = wrp.synth
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local_rank = _dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libwrp has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa_cores = wrp.bind_host_to_gpu(local_rank) if world > 1 and not os.environ.get("WRP_NO_BIND") else []
     if world > 1:
+        wrp.bind_host_to_gpu(local_rank)
         dist.init_process_group("nccl", device_id=dev)
-    S, E = 143, 9
-    U = S * E
-    lo, hi = wrp.volume.shard_bounds(U, rank, world)
-    base = [synth.to_wire(synth.make_sector_int16(M, N, s, 0)) for s in range(8)]
-    pin = wrp.PinnedBuffer((hi - lo) * M * N * 12)
-    view = pin.array.reshape(hi - lo, M * N * 12)
-    for k in range(lo, hi):
-        view[k - lo] = base[k % 8].reshape(-1)
-    chain = wrp.RadarChain(local_rank, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=args.host_piece, n_streams=args.streams)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 1)):
-        vol = wrp.volume.process_volume(chain, pin, U, dev)
-    barrier()
-    l0 = chain.launch_count
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vol = wrp.volume.process_volume(chain, pin, U, dev)
-    barrier()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    v = vol.cpu().numpy()
-    ok = v.shape == (U, M // 2, 2) and np.isfinite(v[:, 1:]).all() and all(
-        np.array_equal(v[k], v[k % 8]) for k in range(0, U, 97))
-    if not ok:
-        raise SystemExit("bench.py: gathered volume is wrong")
+    vol = leg_volume(wrp, args, dev, world, rank, local_rank, max(args.steps, 1))
     if rank == 0:
-        value = U * args.steps / dt
         print(json.dumps({
-            "metric": "sectors_per_s", "value": value, "unit": "sectors/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "metric": "sectors_per_s", "value": vol["value"], "unit": "sectors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": 1, "ms_per_step": vol["ms_per_volume"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "volume scan 9 elevations x 143 sectors, wire int16 from pinned host memory, "
-                                   "contiguous (elevation, sector) shards, product volume all-gathered",
-                       "M": M, "N": N, "channels": C, "units": U},
-            "e2e": {"value": value, "unit": "sectors/s", "h2d_bytes_per_step": U * M * N * 12,
-                    "d2h_bytes_per_step": U * M * 4, "h2d_gbs_per_gpu": value / world * M * N * 12 / 1e9,
-                    "host_cores_bound_per_rank": len(numa_cores)},
-            "volume_bytes": int(v.nbytes), "gpu_launches": int(chain.launch_count - l0)}), flush=True)
+            "config": dict(CONFIG, workload="volume scan 9 elevations x 143 sectors, wire int16 from pinned host memory"),
+            "e2e": {"value": vol["value"], "unit": "sectors/s", "h2d_bytes_per_step": vol["units"] * M * N * 12,
+                    "d2h_bytes_per_step": 0}, "volume": vol, "gpu_launches": vol["gpu_launches"]}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -500,10 +564,13 @@ def main():
     ap.add_argument("--e2e-sectors", type=int, default=143, help="sectors per GPU per step (host leg)")
     ap.add_argument("--host-piece", type=int, default=8, help="sectors per pinned-ring piece")
     ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--sustain-seconds", type=float, default=2.5, help="length of the sustained leg")
     ap.add_argument("--stress-sectors", type=int, default=64,
-                    help="sectors of the 4096x1024 stress shape kept resident for the side figure (0 = skip)")
+                    help="sectors of the 4096x1024 stress shape kept resident per GPU (BASELINE config 5; 0 = skip)")
+    ap.add_argument("--volume-steps", type=int, default=3,
+                    help="volume scans timed for BASELINE config 4 (9 x 143 wire sectors from pinned host memory; 0 = skip)")
     ap.add_argument("--workload", default="sector", choices=["sector", "volume"],
-                    help="sector: the default line (configs 2/3); volume: config 4, one 9 x 143 volume scan, strong scaling")
+                    help="sector: the default line (every leg); volume: only config 4 as its own line")
     ap.add_argument("--cpu-sample", type=int, default=0, help="non-zero: shorten the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "ours":

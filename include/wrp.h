@@ -193,6 +193,11 @@ int wrp_process_device(wrp_handle *h, const void *dev_iq, int n_sectors, float *
  * host_out[n_sectors][M/2][2] is complete. */
 int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *host_out);
 
+/* Same pipeline, but the products stay in device memory: dev_out[n_sectors][M/2][2] on the handle's
+ * device (no D2H).  What a multi-GPU caller uses before gathering the product volume over NVLink
+ * (wrp_volume_process below, volume.py).  Blocks until dev_out is complete. */
+int wrp_process_host_to_device(wrp_handle *h, const void *host_iq, int n_sectors, float *dev_out);
+
 /* Streaming interface mirroring the reference's sector loop (rpv2.cu:665-683):
  * wrp_submit = read_matrix's hand-off + copy_matrix_to_device + the three stages for
  * up to max_batch sectors, tagged with their (sector, elevation) ids (advance(),
@@ -244,6 +249,27 @@ int wrp_pack_products(const float *zdb_zdr, int gates, int sector, int elev, int
                       uint8_t *zdb_packet, uint8_t *zdr_packet);
 
 int wrp_version(void);
+
+/* ---- volume scan over several devices of one box (BASELINE config 4) -----------------
+ * The reference walks (elevation, sector) units one at a time on one GPU (advance(), rpv2.cu:572-579)
+ * and stores unit k = elevation * n_sectors + sector at result[sitdim(0, 0, sector, elevation)]
+ * (rpv2.cu:607, 736).  Units are independent, so a volume is cut into contiguous unit blocks
+ * [ceil(U g / G), ceil(U (g+1) / G)) — one per device, each keeping a contiguous slice of the
+ * reference's result array — with NO data-path collective.  wrp_volume_process runs one host thread
+ * per device (own handle, pinned ring and streams), leaves every device's products in its memory,
+ * gathers the slices into the volume buffer on devices[0] with peer copies (NVLink where the
+ * devices are peers) and returns the volume with one D2H copy.  A device may be listed more than
+ * once (several shards on one GPU). */
+typedef struct wrp_volume wrp_volume;
+int wrp_volume_create(const wrp_config *cfg, const int *devices, int n_devices, int n_sectors, int n_elevations,
+                      wrp_volume **out);
+/* units [*first_unit, *first_unit + *n_units) belong to shard `shard` (0 <= shard < n_devices) */
+int wrp_volume_shard(const wrp_volume *v, int shard, int *first_unit, int *n_units);
+/* host_iq: n_elevations * n_sectors sectors in unit order, configured input_fmt (pinned recommended);
+ * host_volume: [n_elevations][n_sectors][M/2][2] floats = the reference's result[] (rpv2.cu:736). */
+int wrp_volume_process(wrp_volume *v, const void *host_iq, float *host_volume);
+const char *wrp_volume_last_error(const wrp_volume *v);
+void wrp_volume_destroy(wrp_volume *v);
 
 #ifdef __cplusplus
 }

@@ -579,3 +579,82 @@ def test_more_sectors_than_one_launch(wrp, oracle):
     out = d_out.cpu().numpy()
     for i in (0, 1, 2, 500, 1023, 1024, S - 1):
         assert_products_close(out[i], refs_[i % 3].zdb, refs_[i % 3].zdr, f"sector {i} of {S}")
+
+
+def test_radar_processor_udp_loopback(wrp, sectors, refs):
+    """RadarProcessor::set_comms -> start() over real sockets (udpbroadcast.cpp:15-71,
+    radar_processor.cu:59-68): every sector goes in as M datagrams of 12*N = 6144 bytes
+    (read_single.cc:145-148) and its products come back as two 2 + 4*512-byte datagrams
+    [sector BE16][512 BE floats] on the ZdB and ZDR ports (gpu_1fp_streamcasc.cu:709-725)."""
+    import os, socket, subprocess, time
+    exe = os.path.join(os.path.dirname(wrp.LIB_PATH), "host", "wrp_chain")
+    assert os.path.exists(exe), "build the host binaries first (make)"
+
+    def free_port():
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s:
+            s.bind(("127.0.0.1", 0))
+            return s.getsockname()[1]
+
+    p_in, p_zdb, p_zdr = free_port(), free_port(), free_port()
+    rx = []
+    for port in (p_zdb, p_zdr):
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        s.bind(("127.0.0.1", port))
+        s.settimeout(60)
+        rx.append(s)
+    proc = subprocess.Popen([exe, "--udp-in", str(p_in), "--udp-out", f"{p_zdb},{p_zdr}", "--udp-dst", "127.0.0.1",
+                             "--udp-timeout-ms", "4000", "--sectors", "143", "--elevations", "9", "--batch", "1"],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        assert "listening" in proc.stdout.readline()
+        tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        n_sec = 3
+        for k in range(n_sec):
+            wire = wrp.synth.to_wire(sectors[k]).reshape(M, N * 12)
+            for i in range(M):  # one datagram per sweep, paced so that the loopback queue never overflows
+                tx.sendto(wire[i].tobytes(), ("127.0.0.1", p_in))
+                if i % 64 == 63:
+                    time.sleep(0.002)
+        for k in range(n_sec):
+            zb, _ = rx[0].recvfrom(65536)
+            zr, _ = rx[1].recvfrom(65536)
+            assert len(zb) == 2 + 4 * (M // 2) and len(zr) == len(zb)
+            assert int.from_bytes(zb[:2], "big") == k and int.from_bytes(zr[:2], "big") == k
+            out = np.stack([np.frombuffer(zb[2:], ">f4"), np.frombuffer(zr[2:], ">f4")], axis=1).astype(np.float64)
+            assert_products_close(out, refs[k].zdb, refs[k].zdr, f"udp sector {k}")
+        stdout, stderr = proc.communicate(timeout=60)  # the receive timeout ends the sector loop
+        assert proc.returncode == 0, stderr
+        assert f"processed {n_sec} sectors" in stdout
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+        for s in rx:
+            s.close()
+
+
+def test_volume_scan_through_the_c_abi_two_shards(wrp, sectors, refs):
+    """wrp_volume_*: 2 elevations x 5 sectors cut into two contiguous unit blocks, one host thread and one
+    handle per shard (both on device 0 here; on a multi-GPU box pass distinct devices), products gathered
+    on devices[0] by (peer) copies.  The volume equals the reference's sitdim order and the oracle."""
+    S, E = 5, 2
+    wire = np.stack([wrp.synth.to_wire(sectors[(k * 2) % 3]) for k in range(S * E)])
+    n_dev = 1
+    try:
+        import torch
+        n_dev = max(torch.cuda.device_count(), 1)
+    except Exception:
+        pass
+    devices = [0, 1] if n_dev >= 2 else [0, 0]
+    with wrp.VolumeScan(devices, S, E, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=2) as vs:
+        assert vs.shard(0) == (0, 5) and vs.shard(1) == (5, 5)
+        vol = vs.process(wire)
+        again = vs.process(wire)
+    assert np.array_equal(vol, again)
+    for k in range(S * E):
+        r = refs[(k * 2) % 3]
+        assert_products_close(vol[k], r.zdb, r.zdr, f"unit {k}")
+    with wrp.VolumeScan([0, 0, 0], S, E, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=4) as vs3:
+        assert [vs3.shard(g) for g in range(3)] == [(0, 4), (4, 3), (7, 3)]  # ceil(U g / G) blocks
+        vol3 = vs3.process(wire)
+    for k in range(S * E):
+        assert_same_products(vol3[k], vol[k], f"3 shards vs 2, unit {k}")

@@ -75,6 +75,12 @@ class _FakeChain:
             out[i, :, 1] = -float(rec[i, 1])
         return out
 
+    def process_host_to_device(self, host_iq, n, dev_out_ptr):
+        # the "device" of the CPU test is host memory: write the products where the tensor lives
+        import ctypes
+        out = np.ctypeslib.as_array((ctypes.c_float * (n * 4 * 2)).from_address(dev_out_ptr)).reshape(n, 4, 2)
+        self.process_host(host_iq, n, out)
+
 
 def _volume_worker(rank, world, port, units, q):
     import importlib

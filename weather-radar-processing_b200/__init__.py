@@ -46,7 +46,8 @@ EXPORTED_SYMBOLS = (
     "wrp_get_info", "wrp_get_constants", "wrp_process_device", "wrp_process_host",
     "wrp_submit", "wrp_collect", "wrp_alloc_pinned", "wrp_free_pinned", "wrp_dump_stage",
     "wrp_launch_count", "wrp_profile_enable", "wrp_profile_read", "wrp_pack_products",
-    "wrp_chain_kernel_name", "wrp_set_stage02_tap",
+    "wrp_chain_kernel_name", "wrp_set_stage02_tap", "wrp_process_host_to_device",
+    "wrp_volume_create", "wrp_volume_shard", "wrp_volume_process", "wrp_volume_last_error", "wrp_volume_destroy",
 )
 
 
@@ -130,6 +131,14 @@ def lib():
         L.wrp_chain_kernel_name.argtypes = [vp]
         L.wrp_chain_kernel_name.restype = C.c_char_p
         L.wrp_set_stage02_tap.argtypes = [vp, vp]
+        L.wrp_process_host_to_device.argtypes = [vp, vp, ip, vp]
+        L.wrp_volume_create.argtypes = [C.POINTER(Config), C.POINTER(ip), ip, ip, ip, C.POINTER(vp)]
+        L.wrp_volume_shard.argtypes = [vp, ip, C.POINTER(ip), C.POINTER(ip)]
+        L.wrp_volume_process.argtypes = [vp, vp, vp]
+        L.wrp_volume_last_error.argtypes = [vp]
+        L.wrp_volume_last_error.restype = C.c_char_p
+        L.wrp_volume_destroy.argtypes = [vp]
+        L.wrp_volume_destroy.restype = None
         L.wrp_profile_enable.argtypes = [vp, ip]
         L.wrp_profile_read.argtypes = [vp, C.POINTER(Profile), ip]
         L.wrp_pack_products.argtypes = [vp, ip, ip, ip, ip, vp, vp]
@@ -284,6 +293,17 @@ class RadarChain:
         self._check(lib().wrp_process_host(self._h, ptr, n_sectors, out.ctypes.data))
         return out
 
+    def process_host_to_device(self, host_iq, n_sectors: int, dev_out_ptr: int):
+        """Host-buffer batch whose products stay on the device: dev_out_ptr -> float32[n_sectors, M/2, 2]."""
+        if isinstance(host_iq, PinnedBuffer):
+            ptr, nbytes = host_iq.ptr, host_iq.nbytes
+        else:
+            host_iq = np.ascontiguousarray(host_iq)
+            ptr, nbytes = host_iq.ctypes.data, host_iq.nbytes
+        if nbytes < n_sectors * self.input_bytes_per_sector:
+            raise ValueError("input buffer too small")
+        self._check(lib().wrp_process_host_to_device(self._h, ptr, n_sectors, dev_out_ptr))
+
     def submit(self, host_iq, n_sectors: int, sector_ids=None, elev_ids=None):
         if isinstance(host_iq, PinnedBuffer):
             ptr = host_iq.ptr
@@ -329,6 +349,58 @@ class RadarChain:
         p = Profile()
         self._check(lib().wrp_profile_read(self._h, C.byref(p), 1 if reset else 0))
         return p
+
+
+class VolumeScan:
+    """wrp_volume_*: one volume scan (n_elevations x n_sectors units, rpv2.cu:572-579 order) sharded in
+    contiguous unit blocks over the listed devices of this box, one host thread per shard, the product
+    volume gathered on devices[0] by peer copies.  No torch, no NCCL: the C ABI alone."""
+
+    def __init__(self, devices, n_sectors: int, n_elevations: int, **cfg_overrides):
+        self.cfg = default_config(**cfg_overrides)
+        self.devices = list(devices)
+        self.n_sectors, self.n_elevations = n_sectors, n_elevations
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        v = C.c_void_p()
+        rc = lib().wrp_volume_create(C.byref(self.cfg), arr, len(self.devices), n_sectors, n_elevations, C.byref(v))
+        if rc != WRP_OK:
+            raise WrpError(rc, lib().wrp_volume_last_error(None).decode())
+        self._v = v
+
+    def shard(self, g: int) -> tuple[int, int]:
+        lo, n = C.c_int(0), C.c_int(0)
+        rc = lib().wrp_volume_shard(self._v, g, C.byref(lo), C.byref(n))
+        if rc != WRP_OK:
+            raise WrpError(rc, "wrp_volume_shard: bad shard index")
+        return lo.value, n.value
+
+    def process(self, host_iq, out: np.ndarray | None = None) -> np.ndarray:
+        """-> float32[n_elevations * n_sectors, M/2, 2] in the reference's sitdim order."""
+        units = self.n_sectors * self.n_elevations
+        ptr = host_iq.ptr if isinstance(host_iq, PinnedBuffer) else np.ascontiguousarray(host_iq).ctypes.data
+        if out is None:
+            out = np.empty((units, self.cfg.n_rows_M // 2, 2), np.float32)
+        rc = lib().wrp_volume_process(self._v, ptr, out.ctypes.data)
+        if rc != WRP_OK:
+            raise WrpError(rc, lib().wrp_volume_last_error(self._v).decode())
+        return out
+
+    def close(self):
+        if getattr(self, "_v", None):
+            lib().wrp_volume_destroy(self._v)
+            self._v = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_products(zdb_zdr: np.ndarray, sector: int, elev: int = 0, with_elev: bool = True):

@@ -12,6 +12,8 @@
 #include "wrp_chain_params.h"
 #include "wrp_stream.h"
 
+#include <nvtx3/nvToolsExt.h> // header-only: ranges cost nothing unless a profiler is attached
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +30,13 @@ static std::string g_create_error = "";
             return e__ == cudaErrorMemoryAllocation ? WRP_ERR_NOMEM : WRP_ERR_CUDA;           \
         }                                                                                     \
     } while (0)
+
+// NVTX range per C-ABI call on the hot path — the reference's tick()/tock() hook points
+// (gpu_1fp.cu:173-185, 279-286) as profiler ranges
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int fail(wrp_handle *h, int code, const std::string &msg)
 {
@@ -540,6 +549,7 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
 int wrp_process_device(wrp_handle *h, const void *dev_iq, int n_sectors, float *dev_out, void *cuda_stream)
 {
     if (!h) return WRP_ERR_INVALID;
+    NvtxRange r("wrp_process_device");
     if (n_sectors < 0) return fail(h, WRP_ERR_INVALID, "wrp_process_device: negative n_sectors");
     if (n_sectors == 0) return WRP_OK;
     if (!dev_iq || !dev_out) return fail(h, WRP_ERR_INVALID, "wrp_process_device: NULL buffer");
@@ -575,7 +585,7 @@ static bool host_ptr_is_pinned(const void *p)
 
 // enqueue one ring slot: H2D on the slot's copy stream, kernels on the compute stream,
 // D2H back on the slot stream; slot.done fires when the products are in pinned_out.
-static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, int n)
+static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, int n, float *dev_dst = nullptr)
 {
     const wrp_config &c = h->cfg;
     const size_t in_bytes = input_bytes_per_sector(c) * (size_t)n;
@@ -589,13 +599,15 @@ static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, in
     CK(h, cudaMemcpyAsync(s.dev_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
     CK(h, cudaEventRecord(s.h2d_done, s.stream));
     CK(h, cudaStreamWaitEvent(h->compute_stream, s.h2d_done, 0));
-    const int rc = process_device_impl(h, s.dev_in, n, s.dev_out, h->compute_stream);
+    const int rc = process_device_impl(h, s.dev_in, n, dev_dst ? dev_dst : s.dev_out, h->compute_stream);
     if (rc != WRP_OK) return rc;
     CK(h, cudaEventRecord(s.done, h->compute_stream));
-    CK(h, cudaStreamWaitEvent(s.stream, s.done, 0));
-    CK(h, cudaMemcpyAsync(s.pinned_out, s.dev_out, (size_t)n * c.n_rows_M * sizeof(float),
-                          cudaMemcpyDeviceToHost, s.stream));
-    CK(h, cudaEventRecord(s.done, s.stream));
+    if (!dev_dst) { // products back to the host through the slot's pinned buffer
+        CK(h, cudaStreamWaitEvent(s.stream, s.done, 0));
+        CK(h, cudaMemcpyAsync(s.pinned_out, s.dev_out, (size_t)n * c.n_rows_M * sizeof(float),
+                              cudaMemcpyDeviceToHost, s.stream));
+        CK(h, cudaEventRecord(s.done, s.stream));
+    }
     s.n_sectors = n;
     return WRP_OK;
 }
@@ -603,6 +615,7 @@ static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, in
 int wrp_submit(wrp_handle *h, const void *host_iq, int n_sectors, const int *sector_ids, const int *elev_ids)
 {
     if (!h) return WRP_ERR_INVALID;
+    NvtxRange r("wrp_submit");
     if (n_sectors < 1 || n_sectors > h->cfg.max_batch || !host_iq)
         return fail(h, WRP_ERR_INVALID, "wrp_submit: n_sectors must be in [1, max_batch] and host_iq non-NULL");
     if (h->ring_inflight == (int)h->ring.size())
@@ -628,6 +641,7 @@ int wrp_collect(wrp_handle *h, float *out_zdb_zdr, int *sector_ids, int *elev_id
                 int *n_done)
 {
     if (!h || !n_done) return WRP_ERR_INVALID;
+    NvtxRange r("wrp_collect");
     *n_done = 0;
     if (h->ring_inflight == 0) return WRP_OK;
     wrp::RingSlot &s = h->ring[h->ring_tail];
@@ -647,13 +661,9 @@ int wrp_collect(wrp_handle *h, float *out_zdb_zdr, int *sector_ids, int *elev_id
     return WRP_OK;
 }
 
-int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *host_out)
+// host_out != NULL: products to host memory; dev_out != NULL: products stay on the device
+static int process_host_impl(wrp_handle *h, const void *host_iq, int n_sectors, float *host_out, float *dev_out)
 {
-    if (!h) return WRP_ERR_INVALID;
-    if (n_sectors < 0) return fail(h, WRP_ERR_INVALID, "wrp_process_host: negative n_sectors");
-    if (n_sectors == 0) return WRP_OK;
-    if (!host_iq || !host_out) return fail(h, WRP_ERR_INVALID, "wrp_process_host: NULL buffer");
-    if (h->ring_inflight) return fail(h, WRP_ERR_STATE, "wrp_process_host: submissions pending, collect them first");
     CK(h, cudaSetDevice(h->device));
     const wrp_config &c = h->cfg;
     const size_t in_bytes = input_bytes_per_sector(c);
@@ -668,8 +678,9 @@ int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *h
         wrp::RingSlot &s = h->ring[slot];
         if (inflight[slot].n == 0) return WRP_OK;
         CK(h, cudaEventSynchronize(s.done));
-        memcpy(host_out + (size_t)inflight[slot].first * out_floats, s.pinned_out,
-               (size_t)inflight[slot].n * out_floats * sizeof(float));
+        if (host_out)
+            memcpy(host_out + (size_t)inflight[slot].first * out_floats, s.pinned_out,
+                   (size_t)inflight[slot].n * out_floats * sizeof(float));
         inflight[slot].n = 0;
         s.n_sectors = 0;
         return WRP_OK;
@@ -682,7 +693,8 @@ int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *h
         wrp::RingSlot &s = h->ring[slot];
         rc = ensure_slot(h, s);
         if (rc != WRP_OK) return rc;
-        rc = enqueue_slot(h, s, (const uint8_t *)host_iq + (size_t)s0 * in_bytes, n);
+        rc = enqueue_slot(h, s, (const uint8_t *)host_iq + (size_t)s0 * in_bytes, n,
+                          dev_out ? dev_out + (size_t)s0 * out_floats : nullptr);
         if (rc != WRP_OK) return rc;
         inflight[slot] = Piece{s0, n};
     }
@@ -691,6 +703,28 @@ int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *h
         if (rc != WRP_OK) return rc;
     }
     return WRP_OK;
+}
+
+int wrp_process_host(wrp_handle *h, const void *host_iq, int n_sectors, float *host_out)
+{
+    if (!h) return WRP_ERR_INVALID;
+    NvtxRange r("wrp_process_host");
+    if (n_sectors < 0) return fail(h, WRP_ERR_INVALID, "wrp_process_host: negative n_sectors");
+    if (n_sectors == 0) return WRP_OK;
+    if (!host_iq || !host_out) return fail(h, WRP_ERR_INVALID, "wrp_process_host: NULL buffer");
+    if (h->ring_inflight) return fail(h, WRP_ERR_STATE, "wrp_process_host: submissions pending, collect them first");
+    return process_host_impl(h, host_iq, n_sectors, host_out, nullptr);
+}
+
+int wrp_process_host_to_device(wrp_handle *h, const void *host_iq, int n_sectors, float *dev_out)
+{
+    if (!h) return WRP_ERR_INVALID;
+    NvtxRange r("wrp_process_host_to_device");
+    if (n_sectors < 0) return fail(h, WRP_ERR_INVALID, "wrp_process_host_to_device: negative n_sectors");
+    if (n_sectors == 0) return WRP_OK;
+    if (!host_iq || !dev_out) return fail(h, WRP_ERR_INVALID, "wrp_process_host_to_device: NULL buffer");
+    if (h->ring_inflight) return fail(h, WRP_ERR_STATE, "wrp_process_host_to_device: submissions pending, collect them first");
+    return process_host_impl(h, host_iq, n_sectors, nullptr, dev_out);
 }
 
 int wrp_alloc_pinned(size_t bytes, void **out)

@@ -3,6 +3,7 @@
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include <cstring>
@@ -36,6 +37,17 @@ void RadarProcessor::set_comms(int in_port, int *out_ports, int out_length)
         a.sin_family = AF_INET;
         a.sin_addr.s_addr = htonl(INADDR_ANY);
         a.sin_port = htons((uint16_t)in_port);
+        // a sector arrives as a burst of M datagrams (6 MB at the default shape): ask for a receive
+        // buffer that holds one (the kernel clamps the plain option to rmem_max; FORCE needs privileges)
+        int rcvbuf = 32 << 20;
+        if (setsockopt(in_fd_, SOL_SOCKET, SO_RCVBUFFORCE, &rcvbuf, sizeof rcvbuf) < 0)
+            setsockopt(in_fd_, SOL_SOCKET, SO_RCVBUF, &rcvbuf, sizeof rcvbuf);
+        if (recv_timeout_ms_ > 0) {
+            timeval tv;
+            tv.tv_sec = recv_timeout_ms_ / 1000;
+            tv.tv_usec = (recv_timeout_ms_ % 1000) * 1000;
+            setsockopt(in_fd_, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+        }
         if (bind(in_fd_, (sockaddr *)&a, sizeof a) < 0) {
             close(in_fd_);
             in_fd_ = -1;
@@ -77,7 +89,7 @@ void RadarProcessor::udp_sink(int sector, const float *slot, int gates)
         std::memset(&a, 0, sizeof a);
         a.sin_family = AF_INET;
         a.sin_port = htons((uint16_t)out_ports_[i]);
-        a.sin_addr.s_addr = htonl(INADDR_BROADCAST);
+        a.sin_addr.s_addr = out_ip_.empty() ? htonl(INADDR_BROADCAST) : inet_addr(out_ip_.c_str());
         sendto(out_fds_[i], pk[i]->data(), pk[i]->size(), 0, (sockaddr *)&a, sizeof a);
     }
 }

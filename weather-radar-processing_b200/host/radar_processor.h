@@ -40,6 +40,11 @@ class RadarProcessor {
     void set_sink(Sink s) { sink_ = std::move(s); }
     void set_device(int device) { device_ = device; }
     void set_sectors_per_submit(int n) { batch_ = n < 1 ? 1 : n; }
+    // UDP endpoints (set_comms): products go to `ip` instead of INADDR_BROADCAST (udpbroadcast.cpp:24-27);
+    // a receive that stays silent for `ms` ends the sector loop (the reference blocks forever) — call
+    // both before set_comms
+    void set_out_address(const std::string &ip) { out_ip_ = ip; }
+    void set_recv_timeout_ms(int ms) { recv_timeout_ms_ = ms; }
     const char *last_error() const { return error_.c_str(); }
     // product volume in the reference's sitdim order result[x + 2*gate + sector*M + elev*M*S] (rpv2.cu:736)
     const std::vector<float> &result() const { return result_; }
@@ -56,6 +61,8 @@ class RadarProcessor {
     int in_fd_ = -1;
     std::vector<int> out_fds_;
     std::vector<int> out_ports_;
+    std::string out_ip_;
+    int recv_timeout_ms_ = 0;
     Source source_;
     Sink sink_;
     std::string error_;

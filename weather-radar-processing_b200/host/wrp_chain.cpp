@@ -6,6 +6,9 @@
 //             [--zdb-bin out.bin]      ZdB of every sector as raw floats (the layout error.cpp reads)
 //             [--result-dir DIR]       DIR/99result.<k>.gpu.out per sector
 //             [--dump-dir DIR]         staged mode on the FIRST sector: DIR/NNname.gpu.out for hh
+//   wrp_chain --udp-in 19001 --udp-out 19002,19003 [--udp-dst 127.0.0.1 --udp-timeout-ms 3000]
+//             the reference's live endpoints (RadarProcessor::set_comms, read_single.cc:125-148, 510-520):
+//             one datagram of 12*samples bytes per sweep in, [sector BE16][gates BE floats] out
 //   wrp_chain --error ref.bin got.bin [n]   error.cpp's relative L2
 #include <cstdio>
 #include <cstdlib>
@@ -64,8 +67,26 @@ int main(int argc, char **argv)
         return 0;
     }
     const std::string in = arg(argc, argv, "--in", "");
-    if (in.empty()) return fprintf(stderr, "usage: wrp_chain --in wire.bin [...]\n"), 1;
+    const int udp_in = atoi(arg(argc, argv, "--udp-in", "0"));
+    if (in.empty() && !udp_in) return fprintf(stderr, "usage: wrp_chain --in wire.bin | --udp-in PORT --udp-out P1,P2 [...]\n"), 1;
     const int M = atoi(arg(argc, argv, "--sweeps", "1024")), N = atoi(arg(argc, argv, "--samples", "512"));
+    if (udp_in) {
+        RadarProcessor proc(atoi(arg(argc, argv, "--sectors", "143")), M, N, atoi(arg(argc, argv, "--elevations", "9")),
+                            atoi(arg(argc, argv, "--streams", "3")));
+        proc.set_sectors_per_submit(atoi(arg(argc, argv, "--batch", "1")));
+        int ports[2] = {19002, 19003};
+        sscanf(arg(argc, argv, "--udp-out", "19002,19003"), "%d,%d", &ports[0], &ports[1]);
+        const std::string dst = arg(argc, argv, "--udp-dst", "");
+        if (!dst.empty()) proc.set_out_address(dst);
+        proc.set_recv_timeout_ms(atoi(arg(argc, argv, "--udp-timeout-ms", "0")));
+        proc.set_comms(udp_in, ports, 2);
+        printf("listening on udp %d\n", udp_in);
+        fflush(stdout);
+        const int rc = proc.start();
+        if (rc) return fprintf(stderr, "wrp_chain: %s\n", proc.last_error()), 3;
+        printf("processed %ld sectors\n", proc.sectors_processed());
+        return 0;
+    }
     const std::string dump_dir = arg(argc, argv, "--dump-dir", "");
     if (!dump_dir.empty()) {
         const int rc = dump_first_sector(in, dump_dir, M, N);

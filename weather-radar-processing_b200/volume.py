@@ -73,7 +73,10 @@ def process_volume(chain, shard_input, n_units: int, device, group=None):
     else:
         rank, world = 0, 1
     lo, hi = shard_bounds(n_units, rank, world)
-    local = torch.from_numpy(process_shard(chain, shard_input, hi - lo)).to(device)
+    # the products never visit the host: H2D of the input, chain, and the gather all on the device
+    local = torch.empty((hi - lo, chain.M // 2, 2), dtype=torch.float32, device=device)
+    if hi > lo:
+        chain.process_host_to_device(shard_input, hi - lo, local.data_ptr())
     return local if world == 1 else gather_volume(local, n_units, group)
 
 
