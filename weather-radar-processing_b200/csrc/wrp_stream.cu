@@ -50,12 +50,17 @@ template <int Q, bool WIRE> struct Cfg {
     static constexpr int XBUF = 1024 * Q * PITCH; // exchange buffer; also the landing zone of planar input
     static constexpr int LAND = WIRE ? 1024 * T * 4 : 0; // wire: (I, Q) int16 pairs of the tile
     static constexpr int KPW = 32 / T;            // ka values per warp
-    static constexpr int ROWS_PHASE = 8 * KPW;    // gates a warp stages per fold phase (8 kb x KPW ka)
-    // planar M = 1024: a separate staging buffer, because the warp's region of the exchange buffer is
-    // already receiving the next tile; wire / M = 4096: the region itself (see the kernel)
-    static constexpr bool STAGE_SEPARATE = Q == 1 && !WIRE;
+    // the fold runs in PHASES rounds of 16 / PHASES output rows kb: a warp stages 32 gates per round
+    // (KB_PHASE kb x KPW ka) and every lane reads one of them back
+    static constexpr int PHASES = Q == 1 ? 2 : 4;
+    static constexpr int KB_PHASE = 16 / PHASES;
+    static constexpr int ROWS_PHASE = KB_PHASE * KPW;
+    static_assert(ROWS_PHASE == 32, "one staged gate per lane and round");
+    // planar: a separate staging buffer, because the warp's region of the exchange buffer is already
+    // receiving the next tile; wire: the region itself (the next tile lands in the landing buffer)
+    static constexpr bool STAGE_SEPARATE = !WIRE;
     static constexpr int STAGE = STAGE_SEPARATE ? NW * ROWS_PHASE * PITCH : 0;
-    static constexpr int RPT = 2 * ROWS_PHASE / 32; // gates per thread: 2 (M = 1024) or 4 (M = 4096)
+    static constexpr int RPT = PHASES;            // gates per thread: 2 (M = 1024) or 4 (M = 4096)
     static constexpr bool ACC_SMEM = Q == 4;
     static constexpr int ACC = ACC_SMEM ? RPT * 2 * THREADS * 16 : 0; // [gate slot][chunk][thread] float4
     static constexpr int OFF_LAND = XBUF;
@@ -63,8 +68,9 @@ template <int Q, bool WIRE> struct Cfg {
     static constexpr int OFF_ACC = OFF_STAGE + STAGE;
     static constexpr int OFF_TAB = OFF_ACC + ACC;
     static constexpr int OFF_WRC = OFF_TAB;                      // Q = 1
-    static constexpr int OFF_W4 = OFF_TAB;                       // Q = 4: wr(i)*c [4096]
-    static constexpr int OFF_TW4 = OFF_W4 + 4096 * 4;            //        exp(-2 pi i r / 4096) [1024]
+    static constexpr int OFF_TW4 = OFF_TAB;                      // Q = 4: exp(-2 pi i r / 4096) [1024]
+    // (Q = 4: the window wr(i)*c [4096] stays in global memory — a thread needs the same 16 entries for every
+    // tile and fetches them before it waits for the tile; shared memory holds tile + sums + staging)
     static constexpr int OFF_TWA = Q == 1 ? OFF_WRC + 32 * WRC_ROW : OFF_TW4 + 1024 * 8;
     static constexpr int SMEM = OFF_TWA + 32 * TWA_ROW;
     static_assert((Q == 1 ? 2 : 1) * (SMEM + 1024 + 64) <= 233472, "shared memory per SM");
@@ -158,7 +164,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         if constexpr (Q == 1) {
             copy_rows(K::OFF_WRC, p.wrc_t, 32, 32 * 4, WRC_ROW);
         } else {
-            copy_rows(K::OFF_W4, p.wr4, 1, 4096 * 4, 4096 * 4);
             copy_rows(K::OFF_TW4, p.tw4, 1, 1024 * 8, 1024 * 8);
         }
         copy_rows(K::OFF_TWA, p.tw_a, 32, 32 * 8, TWA_ROW);
@@ -193,22 +198,22 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     const int cw = lane % T, ka_l = lane / T;
     uint8_t *const stage = K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH) : xbuf + warp * 8192;
     uint8_t *wbase[2]; // by parity of kbl (T = 8: s depends on it; T = 4: both entries equal)
+    static_assert(T == 8 || (KPW * 4) % 8 == 0, "T = 4: s(R) = (R >> 2) & 1 must not depend on kbl");
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
         const int s = T == 8 ? ((par << 1) | (ka_l >> 1)) : ((ka_l >> 2) & 1);
         wbase[par] = stage + ka_l * PITCH + (((cw >> 1) ^ s) << 4) + (cw & 1) * 8;
     }
-    // reader: lane reads staged rows R = lane (+ 32 for 32-byte rows); logical chunk q sits at q ^ s(R)
+    // reader: lane reads staged row R = lane of the round; logical chunk q sits at q ^ s(R)
     const int rs = T == 8 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
     const uint8_t *const rbase = stage + lane * PITCH;
-    // gate of fold slot r of this thread (r = phase for M = 1024; r = 2 phase + i for M = 4096)
+    // gate of fold slot r (= round) of this thread: staged row lane = kbl * KPW + ka_l
     auto slot_gate = [&](int r) {
         if constexpr (Q == 1) {
             const int kb = 8 * r + (lane >> 2), ka = 4 * warp + (lane & 3);
             return ka + 32 * kb;
         } else {
-            const int h = r >> 1, i = r & 1;
-            const int kb = 8 * h + (lane >> 3) + 4 * i, ka = 8 * (warp & 3) + (lane & 7);
+            const int kb = 4 * r + (lane >> 3), ka = 8 * (warp & 3) + (lane & 7);
             return 4 * (ka + 32 * kb) + (warp >> 2);
         }
     };
@@ -241,6 +246,16 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         if constexpr (Q == 1) wdj = __ldg(p.wd + col);
         else wdp = __ldg(reinterpret_cast<const float2 *>(p.wd + col0) + tid % (T / 2));
 
+        // M = 4096: the 16 window values of this thread's pre-pass units (the same for every tile), fetched
+        // from global memory while the tile is still in flight
+        float wr4v[Q == 4 ? 4 : 1][4];
+        if constexpr (Q == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wr4v[k][q] = __ldg(p.wr4 + (tid + k * THREADS) / (T / 2) + 1024 * q);
+        }
+
         mbar_wait(&mbar, phase);
         phase ^= 1;
 
@@ -250,11 +265,12 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             // one unit = one row r x two adjacent columns (16-byte accesses); the 1024-point transforms of
             // the four sub-tiles then yield rows 4 k' + k0 of the 4096-point transform
             constexpr int UNITS = 1024 * T / 2;
+            static_assert(UNITS == 4 * THREADS, "four pre-pass units per thread");
             const int cp = tid % (T / 2);
-            const float *wr4 = reinterpret_cast<const float *>(smem + K::OFF_W4);
             const float2 *tw4 = reinterpret_cast<const float2 *>(smem + K::OFF_TW4);
-#pragma unroll 2
-            for (int un = tid; un < UNITS; un += THREADS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int un = tid + k * THREADS;
                 const int r = un / (T / 2);
                 uint8_t *ptr = xbuf + r * PITCH + cp * 16;
                 float4 x[4];
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                 float2 e[4], o[4]; // even / odd column of the pair
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float w = wr4[r + 1024 * q];
+                    const float w = wr4v[k][q];
                     const float wa = w * wdp.x, wb = w * wdp.y;
                     e[q] = cmul2(make_float2(x[q].x, x[q].y), make_float2(wa, wa));
                     o[q] = cmul2(make_float2(x[q].z, x[q].w), make_float2(wb, wb));
@@ -393,22 +409,21 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         }
 
         // ================= fold: stages 03-08 in energy form =================
-        // output kb of (c, ka) is gate Q (ka + 32 kb) + sub, column col.  Two phases of eight kb: stage the
-        // warp's outputs as rows [gate][T columns], read whole rows back, update the gate's seven sums.
-        static_for<2>([&](auto hi_) {
+        // output kb of (c, ka) is gate Q (ka + 32 kb) + sub, column col.  PHASES rounds: stage 32 of the warp's
+        // output rows as [gate][T columns], every lane reads one whole row back and updates the gate's seven sums.
+        static_for<K::PHASES>([&](auto hi_) {
             constexpr int h = decltype(hi_)::value;
-            static_for<8>([&](auto ki) {
+            static_for<K::KB_PHASE>([&](auto ki) {
                 constexpr int kbl = decltype(ki)::value;
-                *reinterpret_cast<float2 *>(wbase[kbl & 1] + kbl * (KPW * PITCH)) = v[8 * h + kbl];
+                *reinterpret_cast<float2 *>(wbase[kbl & 1] + kbl * (KPW * PITCH)) = v[K::KB_PHASE * h + kbl];
             });
             __syncwarp();
-            static_for<RPT / 2>([&](auto ii) {
-                constexpr int i = decltype(ii)::value;
-                constexpr int slot = (RPT / 2) * h + i;
+            {
+                constexpr int slot = h;
                 float2 x[T];
                 static_for<CPR>([&](auto qi) {
                     constexpr int q = decltype(qi)::value;
-                    const float4 w = *reinterpret_cast<const float4 *>(rbase + i * (32 * PITCH) + ((q ^ rs) << 4));
+                    const float4 w = *reinterpret_cast<const float4 *>(rbase + ((q ^ rs) << 4));
                     x[2 * q] = make_float2(w.x, w.y);
                     x[2 * q + 1] = make_float2(w.z, w.w);
                 });
@@ -454,14 +469,11 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
 #pragma unroll
                     for (int q = 0; q < 7; ++q) acc[slot][q] = a7[q];
                 }
-            });
+            }
             __syncwarp();
         });
         if constexpr (WIRE) {
             if (lane == 0) mbar_arrive(&ebar);
-        }
-        if constexpr (!K::STAGE_SEPARATE && !WIRE) {
-            if (has_next) issue_tile(nvp, nt); // staged rows consumed: the region may receive the next tile
         }
 
         // ================= end of the plane (or of this CTA's run): products =================
