@@ -213,6 +213,10 @@ inline void fftwf_execute(fftwf_plan p) { wrp_shim::run_plan(p); }
 inline void fftwf_destroy_plan(fftwf_plan p) { delete p; }
 
 /* observe the dB stage (read.cc:342-343, read_single.cc:469-470) */
+/* (not under nvcc: the reference's GPU variants call log10 in device code, and only need this
+ * header for the init-time transform of the 7 moving-average taps, e.g. gpu_1fp_unistream.cu:405-416) */
+#ifndef __CUDACC__
 #define log10(x) wrp_shim::spy_log10(x)
+#endif
 
 #endif

@@ -191,6 +191,7 @@ static int create_impl(wrp_handle *h)
             h->smax = 1024;
             h->chunk = h->smax;
             CK(h, wrp::stream_setup(M, wire_direct, h->sm_count, &h->stream_max_grid));
+            h->l2_promotion = (c.debug >> 8) & 0x3ff ? (c.debug >> 8) & 0x3ff : 0; // experiment knob: debug = bytes << 8
             if (!wire_direct) { // planar tiles are fetched by TMA: the tensor map of a launch is encoded on the host
                 cudaDriverEntryPointQueryResult q;
                 CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->tma_encode, cudaEnableDefault, &q));
@@ -511,7 +512,7 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 memcpy(p.wcol, h->wcol, sizeof p.wcol);
                 const int wire_direct = c.input_fmt == WRP_FMT_WIRE_I16BE && !h->decode_prepass;
                 CUtensorMap tmap{};
-                if (!wire_direct && !wrp::stream_encode_tensor_map(h->tma_encode, &tmap, chain_in, M, N, (long long)S * C))
+                if (!wire_direct && !wrp::stream_encode_tensor_map(h->tma_encode, &tmap, chain_in, M, N, (long long)S * C, h->l2_promotion))
                     return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the batch (is the device buffer 16-byte aligned?)");
                 CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, tmap, st));
                 h->launches++;

@@ -609,7 +609,8 @@ cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid)
 
 size_t stream_scratch_floats(int M, int max_grid) { return (size_t)max_grid * 2 * 7 * (M / 2); }
 
-bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes)
+bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes,
+                              int l2_promotion_bytes)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -622,7 +623,11 @@ bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *bas
     const cuuint32_t estr[2] = {1, 1};
     // complex floats travel as opaque 8-byte elements
     return ((EncodeFn)encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 l2_promotion_bytes >= 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                 : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                 : l2_promotion_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                             : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

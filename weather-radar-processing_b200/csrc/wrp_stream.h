@@ -47,7 +47,10 @@ cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int cha
                           cudaStream_t st);
 // Encodes the tensor map of one launch (host-side, no CUDA call besides the driver's encoder).
 // encode_fn = cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (libwrp does not link libcuda).
-bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes);
+// l2_promotion_bytes: 0 / 64 / 128 / 256 — the tensor map's L2 promotion: a row segment narrower than that pulls the
+// whole aligned block into L2, so the following tiles of the plane (the same CTA, a few microseconds later) hit
+bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int M, int N, long long planes,
+                              int l2_promotion_bytes);
 const char *stream_kernel_name();
 
 } // namespace wrp
