@@ -228,7 +228,7 @@ def run_reference(args):
                         "the stand-in is oracle/shim/fftw3.h — a CPU baseline, NOT the reference's cuFFT cascade"},
         "cpu_baseline": {"value": v, "unit": "sectors/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "sectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "reference_gpu": reference_gpu_leg() if args.gpus == 1 else None,
+        "reference_gpu": reference_gpu_leg() if args.gpus == 1 and not args.skip_reference_gpu else None,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -570,7 +570,7 @@ def run_ours(args):
             "gpu_launches": int(launches + launches_e2e),
             "clocks": clocks,
             "cpu_baseline": cpu,
-            "reference_gpu": reference_gpu_leg() if world == 1 else None,
+            "reference_gpu": reference_gpu_leg() if world == 1 and not args.skip_reference_gpu else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -622,6 +622,8 @@ def main():
     ap.add_argument("--workload", default="sector", choices=["sector", "volume"],
                     help="sector: the default line (every leg); volume: only config 4 as its own line")
     ap.add_argument("--cpu-sample", type=int, default=0, help="non-zero: shorten the CPU baseline leg (profiling runs)")
+    ap.add_argument("--skip-reference-gpu", action="store_true",
+                    help="do not run the reference's cuFFT program as a side figure (profiling runs: it is a child process)")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)  # timing rule: at least 3 untimed warm-up steps

@@ -398,6 +398,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         __syncwarp();
         if constexpr (K::STAGE_SEPARATE) {
             if (has_next) issue_tile(nvp, nt); // the warp's region is in registers: fetch its share of the next tile
+            // (a TMA L2 prefetch of the tile after next, cp.async.bulk.prefetch.tensor, was measured: +0.5 % on
+            // 1024 x 512, -12 % on 4096 x 1024 — the wait for a tile is transfer time under a busy HBM, not DRAM latency)
         }
         fft_dit<R, -1>(v);
         if (p.x2_tap) { // debug tap (tests): stage 02 rows k < M/2 as the product kernel computes them
