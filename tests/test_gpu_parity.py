@@ -518,10 +518,14 @@ def test_stream_kernel_stage02_tap_matches_oracle(wrp, oracle, m, n, c, S):
 
 
 def test_wire_decode_on_the_load_path_is_bit_exact(wrp):
-    """The streaming kernel decodes big-endian int16 records while loading (sector.cpp:52-62 on the
-    GPU).  Fed the same samples as planar floats and forced onto the same work partition (debug 32),
-    it must produce bit-identical products — for ordinary sectors and for one stuffed with the edge
-    patterns: -32768 (0x8000), 32767, -1, 0x00FF, 0xFF00, 0x0100, 0x7F80."""
+    """The wire kernels decode big-endian int16 records while loading (sector.cpp:52-62 on the GPU).  Fed the
+    same samples, the stage-02 tap of a wire-format handle must equal the tap of a planar handle BIT FOR BIT
+    (the range FFT of a column sees identical floats and runs identical arithmetic) — for ordinary sectors and
+    for one stuffed with the edge patterns -32768 (0x8000), 32767, -1, 0x00FF, 0xFF00, 0x0100, 0x7F80.  Checked
+    for the three-channel kernel (12-column tiles, raw rows by TMA), for the one-channel-per-CTA kernel
+    (4-byte cp.async gather; also what two-channel handles use), and — on the same work partition, debug 32 —
+    down to bit-identical products."""
+    torch = pytest.importorskip("torch")
     iq = [wrp.synth.make_sector_int16(M, N, s, 0) for s in range(2)]
     edge = np.array([-32768, 32767, -1, 255, -256, 256, 0x7F80, 0, 1, -2, 128, -129], np.int16)
     rng = np.random.default_rng(5)
@@ -535,11 +539,26 @@ def test_wire_decode_on_the_load_path_is_bit_exact(wrp):
     sec = wrp.Sector(M, N)
     sec.fromByteArray(wire[2].tobytes())
     assert np.array_equal(sec.hh.reshape(M, N, 2), iq[2][0]) and np.array_equal(sec.vh.reshape(M, N, 2), iq[2][2])
-    with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE, max_batch=3) as w, \
-            wrp.RadarChain(0, max_batch=3, debug=32) as p:
-        assert w.chain_kernel == "chain_stream_kernel" and w.info.kernels_per_chunk == 1  # no decode pre-pass
-        a, b = w.process_host(wire, 3), p.process_host(planar, 3)
-    assert np.array_equal(a, b)
+
+    def run(data, **cfg):
+        tap = torch.zeros((3, 3, M // 2, N, 2), device="cuda")
+        with wrp.RadarChain(0, max_batch=3, **cfg) as ch:
+            ch.set_stage02_tap(tap.data_ptr())
+            out = ch.process_host(data, 3)
+            torch.cuda.synchronize()
+            return out, tap.cpu().numpy(), ch.chain_kernel, ch.info.kernels_per_chunk
+
+    o_p, t_p, k_p, _ = run(planar)
+    o_w3, t_w3, k_w3, n_w3 = run(wire, input_fmt=wrp.FMT_WIRE_I16BE)
+    o_w1, t_w1, k_w1, n_w1 = run(wire, input_fmt=wrp.FMT_WIRE_I16BE, debug=128)
+    o_p32, _, _, _ = run(planar, debug=32)
+    assert (k_p, k_w3, k_w1) == ("chain_stream_kernel", "chain_wire3_kernel", "chain_stream_kernel")
+    assert n_w3 == 1 and n_w1 == 1  # no decode pre-pass
+    assert np.abs(t_p).max() > 0
+    assert np.array_equal(t_w3, t_p) and np.array_equal(t_w1, t_p)
+    assert np.array_equal(o_w1, o_p32)  # same partition, same association of the sums: identical products
+    for s_ in range(3):
+        assert_same_products(o_w3[s_], o_p[s_], f"wire3 vs planar, sector {s_}")
     # and the staged path's decode kernel dumps exactly the samples
     with wrp.RadarChain(0, input_fmt=wrp.FMT_WIRE_I16BE, mode=wrp.MODE_STAGED, max_batch=1) as st:
         st.process_host(wire[2:3], 1)
@@ -554,11 +573,13 @@ def test_stream_kernel_any_batch_size_cuts_planes_correctly(wrp, sectors, refs, 
     the oracle, in both input formats."""
     planar = np.stack([wrp.synth.to_planar(sectors[i % 3]) for i in range(S)])
     wire = np.stack([wrp.synth.to_wire(sectors[i % 3]) for i in range(S)])
-    with wrp.RadarChain(0, max_batch=S) as ch, wrp.RadarChain(0, max_batch=S, input_fmt=wrp.FMT_WIRE_I16BE) as wch:
-        a, b = ch.process_host(planar, S), wch.process_host(wire, S)
+    with wrp.RadarChain(0, max_batch=S) as ch, wrp.RadarChain(0, max_batch=S, input_fmt=wrp.FMT_WIRE_I16BE) as wch, \
+            wrp.RadarChain(0, max_batch=S, input_fmt=wrp.FMT_WIRE_I16BE, debug=128) as w1:
+        a, b, c1 = ch.process_host(planar, S), wch.process_host(wire, S), w1.process_host(wire, S)
     for i in range(S):
         assert_products_close(a[i], refs[i % 3].zdb, refs[i % 3].zdr, f"planar S={S} sector {i}")
-        assert_products_close(b[i], refs[i % 3].zdb, refs[i % 3].zdr, f"wire S={S} sector {i}")
+        assert_products_close(b[i], refs[i % 3].zdb, refs[i % 3].zdr, f"wire (3 channels per CTA) S={S} sector {i}")
+        assert_products_close(c1[i], refs[i % 3].zdb, refs[i % 3].zdr, f"wire (1 channel per CTA) S={S} sector {i}")
 
 
 def test_more_sectors_than_one_launch(wrp, oracle):

@@ -190,16 +190,18 @@ static int create_impl(wrp_handle *h)
             h->decode_prepass = wire && !wire_direct;
             h->smax = 1024;
             h->chunk = h->smax;
-            CK(h, wrp::stream_setup(M, wire_direct, h->sm_count, &h->stream_max_grid));
+            h->wire3 = wire_direct && C == 3 && !(c.debug & 128); // debug 128: keep the one-channel-per-CTA wire kernel (A/B)
+            if (h->wire3) CK(h, wrp::wire3_setup(h->sm_count, &h->stream_max_grid));
+            else CK(h, wrp::stream_setup(M, wire_direct, h->sm_count, &h->stream_max_grid));
             // experiment knob (debug = bytes << 8): tensor-map L2 promotion of the tile loads.  Measured on B200:
             // 128 B no change, 64 B / 256 B slower, on both shapes — left off.
             h->l2_promotion = (c.debug >> 8) & 0x3ff;
-            if (!wire_direct) { // planar tiles are fetched by TMA: the tensor map of a launch is encoded on the host
+            if (!wire_direct || h->wire3) { // planar tiles and raw wire rows are fetched by TMA: the tensor map of a launch is encoded on the host
                 cudaDriverEntryPointQueryResult q;
                 CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->tma_encode, cudaEnableDefault, &q));
                 if (!h->tma_encode) return fail(h, WRP_ERR_CUDA, "wrp_create: the driver does not export cuTensorMapEncodeTiled");
             }
-            const int T = M == 4096 ? 4 : 8, NT = N / T;
+            const int T = (M == 4096 || h->wire3) ? 4 : 8, NT = N / T; // columns per tile
             std::vector<float> ttw(4 * (size_t)NT);
             const double kTwoPi = 6.283185307179586476925286766559;
             for (int tt = 0; tt < NT; tt++)
@@ -214,7 +216,9 @@ static int create_impl(wrp_handle *h)
                     const double a = -kTwoPi * (double)(cc * m) / N, sg = (cc & 1) ? -1.0 : 1.0;
                     h->wcol[m - 1][cc] = make_float2((float)(sg * std::cos(a)), (float)(sg * std::sin(a)));
                 }
-            CK(h, cudaMalloc((void **)&h->stream_scratch, wrp::stream_scratch_floats(M, h->stream_max_grid) * sizeof(float)));
+            const size_t scratch_floats =
+                h->wire3 ? wrp::wire3_scratch_floats(h->stream_max_grid) : wrp::stream_scratch_floats(M, h->stream_max_grid);
+            CK(h, cudaMalloc((void **)&h->stream_scratch, scratch_floats * sizeof(float)));
             CK(h, cudaMalloc((void **)&h->stream_cnt, sizeof(int) * (size_t)h->smax * (C + 1)));
             CK(h, cudaMalloc((void **)&h->power, (size_t)h->smax * C * (M / 2) * sizeof(float)));
         } else if (h->chain == wrp_handle::CHAIN_QUEUE) {
@@ -380,7 +384,7 @@ const char *wrp_chain_kernel_name(const wrp_handle *h)
 {
     if (!h) return "";
     switch (h->chain) {
-    case wrp_handle::CHAIN_STREAM: return wrp::stream_kernel_name();
+    case wrp_handle::CHAIN_STREAM: return h->wire3 ? "chain_wire3_kernel" : wrp::stream_kernel_name();
     case wrp_handle::CHAIN_QUEUE: return "chain_persistent_kernel";
     case wrp_handle::CHAIN_V1: return "range_fft_kernel";
     default: return "staged cascade";
@@ -514,6 +518,14 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 memcpy(p.wcol, h->wcol, sizeof p.wcol);
                 const int wire_direct = c.input_fmt == WRP_FMT_WIRE_I16BE && !h->decode_prepass;
                 CUtensorMap tmap{};
+                if (h->wire3) {
+                    if (!wrp::wire3_encode_tensor_map(h->tma_encode, &tmap, chain_in, N, S))
+                        return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the wire batch (is the device buffer 16-byte aligned?)");
+                    CK(h, wrp::launch_wire3(p, h->stream_max_grid, tmap, st));
+                    h->launches++;
+                    h->prof.sectors += h->profiling ? S : 0;
+                    continue;
+                }
                 if (!wire_direct && !wrp::stream_encode_tensor_map(h->tma_encode, &tmap, chain_in, M, N, (long long)S * C, h->l2_promotion))
                     return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the batch (is the device buffer 16-byte aligned?)");
                 CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, tmap, st));

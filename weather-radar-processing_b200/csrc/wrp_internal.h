@@ -83,6 +83,7 @@ struct wrp_handle {
     // streaming kernel (wrp_stream.cu): no hand-off; partial sums of planes cut by the work partition,
     // per-plane / per-sector arrival counters, row powers [smax][C][M/2]
     int stream_max_grid = 0;
+    bool wire3 = false; // wire input, M = 1024, 3 channels: chain_wire3_kernel (12-column tiles, raw rows by TMA)
     int l2_promotion = 0; // tensor-map L2 promotion of the tile loads, bytes
     void *tma_encode = nullptr; // cuTensorMapEncodeTiled (driver entry point; libwrp does not link libcuda)
     float *stream_scratch = nullptr;

@@ -578,6 +578,297 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     }
 }
 
+
+// ================================================================================================
+// chain_wire3_kernel — wire input (12-byte records hhI hhQ vvI vvQ vhI vhQ, sector.cpp:52-62), M = 1024,
+// three channels, ALL of them in one CTA.
+//
+// A tile = 4 adjacent record columns x 1024 sweeps = 12 FFT columns (4 columns x hh, vv, vh).  Its raw
+// rows (48 bytes) arrive by TMA — four boxes {12 x uint32, 256 rows} — into one of two 48 KiB landing
+// buffers, separate from the exchange buffer, so the load of tile n+1 is issued at the top of tile n and has
+// the whole tile's work to land (chain_stream_kernel<1, true> gathers one channel with 4-byte cp.async, which
+// the LSU handles element by element: 0.74 TB/s, tools/micro/tile_load.cu; TMA cannot gather below 16 bytes,
+// raw rows come in at 4.3 TB/s).  384 threads, one CTA per SM:
+//   pass 1  thread (c2, b), c2 = record column * 3 + channel = position of the (I, Q) pair in the raw row:
+//           rows 32 a + b, big-endian decode, window in the first butterfly stage, radix-32, twiddle,
+//           exchange buffer [32 ka groups][32 rows][96 B] with 96 B of padding per group (conflict-free)
+//   pass 2  warp = (channel, 8 ka), lane = (ka, column): radix-32 over b, outputs k < 512
+//   fold    as chain_stream_kernel's M = 4096 form (4-column rows, four rounds, warp-local staging); a thread
+//           owns four (gate, channel) rows: 28 accumulators in registers
+//   sector end: P[k] per channel -> power[], ZdB/ZDR from hh and vv by the same CTA (rpv2.cu:199-213); a sector
+//           cut by the work partition is summed by the last CTA to arrive, parts in CTA order.
+// No CTA waits for another.
+namespace w3 {
+constexpr int THREADS = 384, NWARP = 12, COLS = 12, RC = 4; // record columns per tile
+constexpr int RAW_PITCH = 48, RAW_BYTES = 1024 * RAW_PITCH;
+constexpr int XROW = 96, XGROUP = 32 * XROW + 96, XBUF = 32 * XGROUP;
+constexpr int STAGE_WARP = 32 * 32, STAGE = NWARP * STAGE_WARP;
+constexpr int OFF_RAW = 0, OFF_X = 2 * RAW_BYTES, OFF_STAGE = OFF_X + XBUF, OFF_WRC = OFF_STAGE + STAGE;
+constexpr int OFF_TWA = OFF_WRC + 32 * WRC_ROW, OFF_BAR = OFF_TWA + 32 * TWA_ROW, SMEM = OFF_BAR + 64;
+static_assert(SMEM <= 232448, "shared memory per CTA");
+} // namespace w3
+
+__global__ void __launch_bounds__(w3::THREADS, 1)
+    chain_wire3_kernel(const StreamParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    using namespace w3;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *const rbar = reinterpret_cast<uint64_t *>(smem + OFF_BAR);     // [2] raw tile landed
+    uint64_t *const ebar = reinterpret_cast<uint64_t *>(smem + OFF_BAR + 16); // every warp has read its pass-2 operands
+    int *const s_flag = reinterpret_cast<int *>(smem + OFF_BAR + 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hm = 512;
+
+    // work partition: a contiguous run of tiles of the [sector][tile] space
+    const int NT = p.N / RC;
+    const long long total = (long long)p.S * NT;
+    const int G = gridDim.x;
+    const int g_lo = (int)((long long)blockIdx.x * total / G), g_end = (int)(((long long)blockIdx.x + 1) * total / G);
+    if (g_lo >= g_end) return;
+    auto cta_of = [&](long long g) { return (int)(((g + 1) * G - 1) / total); };
+
+    for (int i = tid; i < 32 * 8; i += THREADS) // 16-byte pieces of the window table
+        *reinterpret_cast<float4 *>(smem + OFF_WRC + (i >> 3) * WRC_ROW + (i & 7) * 16) =
+            __ldg(reinterpret_cast<const float4 *>(p.wrc_t) + i);
+    for (int i = tid; i < 32 * 16; i += THREADS)
+        *reinterpret_cast<float4 *>(smem + OFF_TWA + (i >> 4) * TWA_ROW + (i & 15) * 16) =
+            __ldg(reinterpret_cast<const float4 *>(p.tw_a) + i);
+    if (tid == 0) {
+        mbar_init(&rbar[0], 1);
+        mbar_init(&rbar[1], 1);
+        mbar_init(ebar, NWARP);
+    }
+    __syncthreads();
+
+    int sector = g_lo / NT, t = g_lo - sector * NT;
+    const int sector_lo = sector;
+    auto issue_raw = [&](int sec, int tile, int buf) { // thread 0: four boxes of 256 sweeps x 48 bytes
+        mbar_expect_tx(&rbar[buf], RAW_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            tma_load_2d(smem + OFF_RAW + buf * RAW_BYTES + q * (256 * RAW_PITCH), &tmap, tile * COLS, sec * 1024 + q * 256,
+                        &rbar[buf]);
+    };
+    if (tid == 0) issue_raw(sector, t, 0);
+
+    // pass-1 identity: c2 = position of the thread's (I, Q) pair in the raw row, b = row residue
+    const int c2 = tid % COLS, b1 = tid / COLS;
+    // pass-2 / fold identity: warp = (channel, group of eight ka), lane = (ka, column)
+    const int ch = warp >> 2, kag = warp & 3, ka_l = lane >> 2, colw = lane & 3;
+    const int ka = 8 * kag + ka_l;
+    uint8_t *const stage = smem + OFF_STAGE + warp * STAGE_WARP;
+    // staged row R = kbl * 8 + ka_l (32-byte rows); 16-byte chunk (col >> 1) XOR s(R), s(R) = (R >> 2) & 1
+    uint8_t *const wbase = stage + ka_l * 32 + ((((colw >> 1) ^ ((ka_l >> 2) & 1))) << 4) + (colw & 1) * 8;
+    const int rs = (lane >> 2) & 1;
+    const uint8_t *const rbase = stage + lane * 32;
+    auto slot_gate = [&](int r) { return 8 * kag + (lane & 7) + 32 * (4 * r + (lane >> 3)); };
+    float acc[4][7];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) acc[r][q] = 0.f;
+
+    uint32_t ephase = 0;
+    int n = 0;
+    for (int g = g_lo; g < g_end; ++g, ++n) {
+        int nt = t + 1, nsector = sector;
+        if (nt == NT) nt = 0, ++nsector;
+        const bool has_next = g + 1 < g_end;
+        const int buf = n & 1;
+        // the other landing buffer was last read in pass 1 of the previous tile, and every thread has passed
+        // that tile's exchange barrier: request the next tile now, a whole tile ahead
+        if (tid == 0 && has_next) issue_raw(nsector, nt, buf ^ 1);
+        const float4 ttw = __ldg(p.tile_tw + t);
+        const float wdj = __ldg(p.wd + t * RC + c2 / 3);
+
+        mbar_wait(&rbar[buf], (n >> 1) & 1);
+
+        // ================= pass 1 =================
+        float2 v[R];
+        {
+            const uint8_t *src = smem + OFF_RAW + buf * RAW_BYTES + b1 * RAW_PITCH + c2 * 4;
+            static_for<R>([&](auto ai) {
+                constexpr int a = decltype(ai)::value;
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(src + a * (R * RAW_PITCH));
+                v[brev<R>(a)] = make_float2((float)(int)prmt(w, 0u, 0x8801u), (float)(int)prmt(w, 0u, 0xAA23u));
+            });
+        }
+        {
+            const float2 m2 = make_float2(-2.f, -2.f);
+            const float4 *w4 = reinterpret_cast<const float4 *>(smem + OFF_WRC + b1 * WRC_ROW);
+            static_for<R / 8>([&](auto qi) {
+                constexpr int q = decltype(qi)::value;
+                const float4 wlo = w4[q], whi = w4[q + R / 8];
+                const float lo[4] = {wlo.x, wlo.y, wlo.z, wlo.w}, hi[4] = {whi.x, whi.y, whi.z, whi.w};
+                static_for<4>([&](auto ei) {
+                    constexpr int e = decltype(ei)::value;
+                    constexpr int sa = brev<R>(4 * q + e);
+                    const float wl = lo[e] * wdj, wh = hi[e] * wdj;
+                    const float2 tt = cmul2(v[sa + 1], make_float2(wh, wh));
+                    const float2 s2 = cfma2(v[sa], make_float2(wl, wl), tt);
+                    v[sa + 1] = cfma2(tt, m2, s2);
+                    v[sa] = s2;
+                });
+            });
+            fft_dit_after_stage1<R, -1>(v);
+        }
+        if (n > 0) { // every warp has pulled its pass-2 operands of the previous tile out of the exchange buffer
+            mbar_wait(ebar, ephase);
+            ephase ^= 1;
+        }
+        {
+            const float4 *t4 = reinterpret_cast<const float4 *>(smem + OFF_TWA + b1 * TWA_ROW);
+            uint8_t *dst = smem + OFF_X + b1 * XROW + c2 * 8;
+            float4 wq[3] = {t4[0], t4[1], t4[2]};
+            static_for<R / 2>([&](auto qi) {
+                constexpr int q = decltype(qi)::value;
+                const float4 w = wq[q % 3];
+                if constexpr (q + 3 < R / 2) wq[q % 3] = t4[q + 3];
+                const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
+                const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
+                *reinterpret_cast<float2 *>(dst + (2 * q) * XGROUP) = y0;
+                *reinterpret_cast<float2 *>(dst + (2 * q + 1) * XGROUP) = y1;
+            });
+        }
+        __syncthreads(); // the exchange
+
+        // ================= pass 2 =================
+        {
+            const uint8_t *src = smem + OFF_X + ka * XGROUP + (colw * 3 + ch) * 8;
+            static_for<R>([&](auto bi) {
+                constexpr int bb = decltype(bi)::value;
+                v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(src + bb * XROW);
+            });
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ebar);
+        fft_dit<R, -1>(v);
+        const int col = t * RC + colw;
+        if (p.x2_tap) {
+            float2 *o = p.x2_tap + ((size_t)(sector * 3 + ch) * hm + ka) * (size_t)p.N + col;
+            static_for<R / 2>([&](auto ki) {
+                constexpr int kb = decltype(ki)::value;
+                o[(size_t)(R * kb) * p.N] = v[kb];
+            });
+        }
+
+        // ================= fold =================
+        static_for<4>([&](auto hi_) {
+            constexpr int h = decltype(hi_)::value;
+            static_for<4>([&](auto ki) {
+                constexpr int kbl = decltype(ki)::value;
+                *reinterpret_cast<float2 *>(wbase + kbl * (8 * 32)) = v[4 * h + kbl];
+            });
+            __syncwarp();
+            {
+                float2 x[4];
+                static_for<2>([&](auto qi) {
+                    constexpr int q = decltype(qi)::value;
+                    const float4 w = *reinterpret_cast<const float4 *>(rbase + ((q ^ rs) << 4));
+                    x[2 * q] = make_float2(w.x, w.y);
+                    x[2 * q + 1] = make_float2(w.z, w.w);
+                });
+                float2 e2 = cmul2(x[0], x[0]);
+                float2 s0 = x[0], s1 = x[0], s2 = x[0];
+                static_for<3>([&](auto ci) {
+                    constexpr int cc = decltype(ci)::value + 1;
+                    e2 = cfma2(x[cc], x[cc], e2);
+                    s0 = cadd(s0, x[cc]);
+                    const float2 w1 = p.wcol[0][cc], w2 = p.wcol[1][cc];
+                    s1.x = fmaf(x[cc].x, w1.x, s1.x);
+                    s1.x = fmaf(-x[cc].y, w1.y, s1.x);
+                    s1.y = fmaf(x[cc].x, w1.y, s1.y);
+                    s1.y = fmaf(x[cc].y, w1.x, s1.y);
+                    s2.x = fmaf(x[cc].x, w2.x, s2.x);
+                    s2.x = fmaf(-x[cc].y, w2.y, s2.x);
+                    s2.y = fmaf(x[cc].x, w2.y, s2.y);
+                    s2.y = fmaf(x[cc].y, w2.x, s2.y);
+                });
+                acc[h][0] += e2.x + e2.y;
+                acc[h][1] += s0.x;
+                acc[h][2] += s0.y;
+                acc[h][3] = fmaf(s1.x, ttw.x, acc[h][3]);
+                acc[h][3] = fmaf(-s1.y, ttw.y, acc[h][3]);
+                acc[h][4] = fmaf(s1.x, ttw.y, acc[h][4]);
+                acc[h][4] = fmaf(s1.y, ttw.x, acc[h][4]);
+                acc[h][5] = fmaf(s2.x, ttw.z, acc[h][5]);
+                acc[h][5] = fmaf(-s2.y, ttw.w, acc[h][5]);
+                acc[h][6] = fmaf(s2.x, ttw.w, acc[h][6]);
+                acc[h][6] = fmaf(s2.y, ttw.z, acc[h][6]);
+            }
+            __syncwarp();
+        });
+
+        // ================= end of the sector (or of this CTA's run) =================
+        if (nt == 0 || !has_next) {
+            const long long sector_first = (long long)sector * NT;
+            const bool complete = g_lo <= sector_first && nt == 0;
+            float vals[4][7];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    vals[r][q] = acc[r][q];
+                    acc[r][q] = 0.f;
+                }
+            bool finalize = complete;
+            if (!complete) {
+                float *mine = p.scratch + (((size_t)blockIdx.x * 2 + (sector == sector_lo ? 0 : 1)) * 3 + ch) * 7 * hm;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int k = slot_gate(r);
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) mine[q * hm + k] = vals[r][q];
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) *s_flag = atomicAdd(p.plane_cnt + sector, 1);
+                __syncthreads();
+                const int x_first = cta_of(sector_first), x_last = cta_of(sector_first + NT - 1);
+                if (*s_flag == x_last - x_first) {
+                    __threadfence();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) vals[r][q] = 0.f;
+                    for (int x = x_first; x <= x_last; ++x) {
+                        const int x_sector_lo = (int)(((long long)x * total / G) / NT);
+                        const float *part = p.scratch + (((size_t)x * 2 + (sector == x_sector_lo ? 0 : 1)) * 3 + ch) * 7 * hm;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int k = slot_gate(r);
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) vals[r][q] += __ldcg(part + q * hm + k);
+                        }
+                    }
+                    finalize = true;
+                }
+            }
+            if (finalize) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int k = slot_gate(r);
+                    float removed = vals[r][1] * vals[r][1];
+#pragma unroll
+                    for (int q = 2; q < 7; ++q) removed = fmaf(vals[r][q], vals[r][q], removed);
+                    p.power[((size_t)sector * 3 + ch) * hm + k] =
+                        fmaxf(fmaf(p.n_float, vals[r][0], -removed), 0.f) * p.taps_sum;
+                }
+                __syncthreads(); // hh and vv of a gate were written by different warps of this CTA
+                const float *ph = p.power + (size_t)sector * 3 * hm, *pv = ph + hm;
+                for (int k = tid; k < hm; k += THREADS) {
+                    const float hh = ph[k], vv = pv[k];
+                    const float rg = (float)k * p.range_res;
+                    reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
+                        make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv)));
+                }
+            }
+        }
+        t = nt;
+        sector = nsector;
+    }
+}
+
 } // namespace stream
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -601,6 +892,51 @@ template <int Q, bool WIRE> static cudaError_t setup_one(int sm_count, int *max_
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     *max_grid = per_sm * sm_count;
     return cudaSuccess;
+}
+
+cudaError_t wire3_setup(int sm_count, int *max_grid)
+{
+    cudaError_t e = cudaFuncSetAttribute(stream::chain_wire3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stream::w3::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream::chain_wire3_kernel, stream::w3::THREADS, stream::w3::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *max_grid = per_sm * sm_count;
+    return cudaSuccess;
+}
+
+size_t wire3_scratch_floats(int max_grid) { return (size_t)max_grid * 2 * 3 * 7 * 512; }
+
+bool wire3_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int N, long long sectors)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    if (!encode_fn) return false;
+    // the batch as a [sectors * 1024 sweeps][3 N] matrix of 32-bit (I, Q) pairs; box = 12 pairs (4 records) x 256 sweeps
+    const cuuint64_t dims[2] = {(cuuint64_t)N * 3, (cuuint64_t)sectors * 1024};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 12};
+    const cuuint32_t box[2] = {12, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    return ((EncodeFn)encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_wire3(StreamParams p, int max_grid, const CUtensorMap &tmap, cudaStream_t st)
+{
+    if (p.S <= 0) return cudaSuccess;
+    p.NT = p.N / 4;
+    p.half_m = 512;
+    p.n_float = (float)p.N;
+    p.chan_groups = 1;
+    const long long total = (long long)p.S * p.NT;
+    const int grid = (int)(max_grid < total ? max_grid : total);
+    cudaError_t e = cudaMemsetAsync(p.plane_cnt, 0, sizeof(int) * (size_t)p.S, st); // parts of a cut sector that have arrived
+    if (e != cudaSuccess) return e;
+    stream::chain_wire3_kernel<<<grid, stream::w3::THREADS, stream::w3::SMEM, st>>>(p, tmap);
+    return cudaGetLastError();
 }
 
 cudaError_t stream_setup(int M, int wire, int sm_count, int *max_grid)

@@ -53,4 +53,11 @@ bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *bas
                               int l2_promotion_bytes);
 const char *stream_kernel_name();
 
+// chain_wire3_kernel: wire records, M = 1024, three channels in one CTA (12-column tiles, raw rows by TMA).
+// tile_tw / wcol must be built for 4-column tiles.
+cudaError_t wire3_setup(int sm_count, int *max_grid);
+size_t wire3_scratch_floats(int max_grid);
+bool wire3_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int N, long long sectors);
+cudaError_t launch_wire3(StreamParams p, int max_grid, const CUtensorMap &tmap, cudaStream_t st);
+
 } // namespace wrp
