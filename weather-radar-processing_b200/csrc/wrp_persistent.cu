@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 if (!ready) ready = ld_relaxed(probe_dep) >= probe_target; // the early probe may be stale
                 if ((p.debug & 16) && cand.kind >= 0 && !ready) atomicAdd(p.ctrl + 1 + cand.kind, 1);
                 s_item[nslot] = make_int4(cand.kind, cand.sector, cand.sub, cand.slot);
-                if (ready) s_go = n + 2; // before s_seq: whoever sees the item also sees that it may load
+                if (ready) {
+                    fence_acquire_gpu(); // one fence per item from one thread
+                    s_go = n + 2;        // before s_seq: whoever sees the item also sees that it may load
+                }
                 __threadfence_block();
                 s_seq = n + 2;
             }
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 }
             }
             if (!p.discard) {
-                if (tid == 0) atomicAdd(p.ctrl + CTRL_A + p.smax + it.sector, 1);
+                if (tid == 0) red_release_add(p.ctrl + CTRL_A + p.smax + it.sector);
             } else {
                 pending_b = it.sector; // reported after this item's first pass, when the discards have drained
             }

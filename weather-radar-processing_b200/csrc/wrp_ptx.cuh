@@ -103,10 +103,19 @@ __device__ __forceinline__ int ld_relaxed(const int *p)
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Bounded: a dependency that never arrives (a kernel bug, a corrupted counter) must end as a device error —
+// cudaErrorLaunchFailure -> WRP_ERR_CUDA at the next API call — not as a hung GPU.  2^26 probes x >= 100 ns
+// is several seconds, three orders of magnitude beyond the longest legitimate wait (one work item).
 __device__ __forceinline__ void spin_until(const int *p, int target)
 {
-    while (ld_acquire(p) < target) __nanosleep(100);
+    for (unsigned spins = 0; ld_acquire(p) < target; ++spins) {
+        if (spins >> 26) __trap();
+        __nanosleep(100);
+    }
 }
+// pairs a successful relaxed probe with the producer's red.release: data read after it (cp.async.cg from L2)
+// is ordered behind the counter value in the PTX memory model, not only in practice
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // L2 evict-last policy and an 8-byte store carrying it (experiments on keeping the x2 ring resident)
 __device__ __forceinline__ uint64_t policy_evict_last()
