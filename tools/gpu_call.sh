@@ -1,13 +1,9 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/s15_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/s15_tests.log
-timeout 600 python tools/sanitize_case.py > gpurun_out/s15_small_cases.log 2>&1; echo "small cases rc=$?"; tail -2 gpurun_out/s15_small_cases.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-CMD="python bench.py --steps 2 --warmup 3 --cpu-sample 1 --sustain-seconds 0.001 --stress-sectors 8 --volume-steps 0 --skip-reference-gpu"
-$CMD > gpurun_out/s15_plain1.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/s15_ncu1.log 2>&1
-timeout 900 python bench.py > gpurun_out/s15_bench.json 2> gpurun_out/s15_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/s15_bench.err
-python - <<'PY'
+N=${NGPU:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/s16_bench_n$N.json 2> gpurun_out/s16_bench_n$N.err; echo "bench n$N rc=$?"; tail -2 gpurun_out/s16_bench_n$N.err
+python - <<PY
 import json
-d=json.load(open('gpurun_out/s15_bench.json'))
-print({k:d[k] for k in ('value','chain_hbm_frac')}, 'sustained', d['sustained']['value'], 'stress', d['stress']['hbm_frac'], 'volume', d['volume']['value'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_h2d_ceiling'], 'wire', d['wire_resident']['value'], 'refgpu', d['reference_gpu'].get('value'))
+d=json.load(open('gpurun_out/s16_bench_n$N.json'))
+print('N',d['n_gpus'],'value',round(d['value']),'ms/step',round(d['ms_per_step'],4),'share',round(d['roofline']['kernel_share_of_step'],4),'gathers',d['run']['gathers_in_timed_region'],'sustained',round(d['sustained']['value']),'stress',round(d['stress']['value']),round(d['stress']['hbm_frac'],3),'volume',round(d['volume']['value']),'e2e',round(d['e2e']['value']),round(d['e2e']['h2d_ceiling_gbs'],1),round(d['e2e']['frac_of_h2d_ceiling'],3))
 PY
+timeout 600 python tools/volume_cabi.py --gpus $N --elevations 9 2>&1 | tail -1 | tee gpurun_out/s16_volume_cabi_n$N.json
