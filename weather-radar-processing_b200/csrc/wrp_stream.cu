@@ -59,12 +59,18 @@ template <int Q, bool WIRE> struct Cfg {
     // planar: a separate staging buffer, because the warp's region of the exchange buffer is already
     // receiving the next tile; wire: the region itself (the next tile lands in the landing buffer)
     static constexpr bool STAGE_SEPARATE = !WIRE;
-    static constexpr int STAGE = STAGE_SEPARATE ? NW * ROWS_PHASE * PITCH : 0;
+    // planar M = 1024: the lower half of the exchange (ka < 16) goes to its own 32 KiB buffer, so rows 0..511 of
+    // the tile buffer are dead after the pass-1 reads and are requested again right then (58 % of a tile's work
+    // earlier than the upper half, which is exchanged in place); the fold stages inside that buffer
+    static constexpr bool EARLY = Q == 1 && !WIRE;
+    static constexpr int XLO = EARLY ? 512 * PITCH : 0;
+    static constexpr int STAGE = (STAGE_SEPARATE && !EARLY) ? NW * ROWS_PHASE * PITCH : 0;
     static constexpr int RPT = PHASES;            // gates per thread: 2 (M = 1024) or 4 (M = 4096)
     static constexpr bool ACC_SMEM = Q == 4;
     static constexpr int ACC = ACC_SMEM ? RPT * 2 * THREADS * 16 : 0; // [gate slot][chunk][thread] float4
     static constexpr int OFF_LAND = XBUF;
-    static constexpr int OFF_STAGE = OFF_LAND + LAND;
+    static constexpr int OFF_XLO = OFF_LAND + LAND;
+    static constexpr int OFF_STAGE = OFF_XLO + XLO;
     static constexpr int OFF_ACC = OFF_STAGE + STAGE;
     static constexpr int OFF_TAB = OFF_ACC + ACC;
     static constexpr int OFF_WRC = OFF_TAB;                      // Q = 1
@@ -135,8 +141,9 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar; // the next tile has landed: planar — one arrival + 8 KiB of TMA bytes per warp;
                                            // wire — one arrival per thread, fired by its cp.asyncs
-    __shared__ __align__(8) uint64_t ebar; // wire: every warp is done with its staged rows of the previous tile
-    __shared__ int s_flag;
+    __shared__ __align__(8) uint64_t ebar; // wire / early: every warp is done with its staged rows of the previous tile
+    __shared__ __align__(8) uint64_t lobar; // early: warps 0-3 have read their pass-2 operands out of the lower exchange buffer
+    __shared__ int s_flag, s_rdcnt;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *const xbuf = smem;
@@ -173,8 +180,10 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         }
     }
     if (tid == 0) {
-        mbar_init(&mbar, WIRE ? THREADS : NW);
+        mbar_init(&mbar, WIRE ? THREADS : (K::EARLY ? NW / 2 + 1 : NW));
         mbar_init(&ebar, NW);
+        mbar_init(&lobar, NW / 2);
+        s_rdcnt = 0;
     }
     __syncthreads();
 
@@ -189,14 +198,26 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             issue_tile_planar<Q, WIRE>(&tmap, xbuf, &mbar, plane, tile, warp, lane);
         }
     };
-    issue_tile(vp, t);
+    if constexpr (K::EARLY) { // same arrival pattern as every later tile: one for rows 0..511, one per warp 4-7
+        if (warp >= NW / 2) {
+            issue_tile(vp, t);
+        } else if (tid == 0) {
+            mbar_expect_tx(&mbar, 4 * 8192);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tma_load_2d(xbuf + q * 8192, &tmap, t * T, real_plane(vp) * 1024 + q * 128, &mbar);
+        }
+    } else {
+        issue_tile(vp, t);
+    }
 
     // ---- per-thread constants of the fold ---------------------------------------------------------
     // writer: thread (column c, ka_l) stores output kb of the phase at staged row R = kbl * KPW + ka_l;
     // 16-byte chunk (c >> 1) of a row is XOR-swizzled with s(R) so that the 128-bit row reads below are
     // conflict-free: s(R) = (R >> 1) & 3 for 64-byte rows, (R >> 2) & 1 for 32-byte rows
     const int cw = lane % T, ka_l = lane / T;
-    uint8_t *const stage = K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH) : xbuf + warp * 8192;
+    uint8_t *const stage = K::EARLY            ? smem + K::OFF_XLO + warp * (K::ROWS_PHASE * PITCH)
+                           : K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH)
+                                               : xbuf + warp * 8192;
     uint8_t *wbase[2]; // by parity of kbl (T = 8: s depends on it; T = 4: both entries equal)
     static_assert(T == 8 || (KPW * 4) % 8 == 0, "T = 4: s(R) = (R >> 2) & 1 must not depend on kbl");
 #pragma unroll
@@ -226,8 +247,9 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     }
     float4 *const acc_s = reinterpret_cast<float4 *>(smem + K::OFF_ACC) + tid; // [slot][chunk][thread]
 
-    uint32_t phase = 0, ephase = 0;
+    uint32_t phase = 0, ephase = 0, lophase = 0;
     bool first = true;
+    int n_tile = 0; // tiles this CTA has started
 
     for (int g = g_lo; g < g_end; ++g) {
         int nt = t + 1, nvp = vp;
@@ -321,6 +343,19 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                 v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
             });
         }
+        if constexpr (K::EARLY) {
+            // the last warp to have read the tile requests rows 0..511 of the next one (the regions of warps 0-3)
+            __syncwarp();
+            if (lane == 0) {
+                const int old = atomicAdd(&s_rdcnt, 1);
+                if (old == NW * n_tile + NW - 1 && has_next) {
+                    mbar_expect_tx(&mbar, 4 * 8192);
+                    const int np = real_plane(nvp);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tma_load_2d(xbuf + q * 8192, &tmap, nt * T, np * 1024 + q * 128, &mbar);
+                }
+            }
+        }
         if constexpr (Q == 1) {
             // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage: the span-1
             // partners of the bit-reversed network are rows a and a + 16
@@ -345,8 +380,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         } else {
             fft_dit<R, -1>(v);
         }
-        if constexpr (WIRE) {
-            // the exchange buffer doubles as the fold's staging area: wait until every warp has read its
+        if constexpr (WIRE || K::EARLY) {
+            // the (lower) exchange buffer doubles as the fold's staging area: wait until every warp has read its
             // staged rows of the previous tile back before overwriting them
             if (!first) {
                 mbar_wait(&ebar, ephase);
@@ -360,6 +395,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             uint8_t *d_sw[SW + 1];
 #pragma unroll
             for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = stile + (b ^ sx) * PITCH + c * 8;
+            // early: rows 32 ka + .. with ka < 16 live in the lower exchange buffer (same row map)
+            const ptrdiff_t lo_shift = K::EARLY ? (smem + K::OFF_XLO) - stile : 0;
             float4 wq[3] = {t4[0], t4[1], t4[2]};
             static_for<R / 2>([&](auto qi) {
                 constexpr int q = decltype(qi)::value;
@@ -367,8 +404,9 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                 if constexpr (q + 3 < R / 2) wq[q % 3] = t4[q + 3];
                 const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
                 const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
-                *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
-                *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
+                constexpr bool lo = K::EARLY && 2 * q + 1 < 16;
+                *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH) + (lo ? lo_shift : 0)) = y0;
+                *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH) + (lo ? lo_shift : 0)) = y1;
             });
         }
         // the exchange: the one barrier of a 1024-point column group
@@ -388,15 +426,22 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         const int ka = b; // rows 32 ka + .. of warp w are its own 8 KiB region
         {
             const uint8_t *s_sw[SW + 1];
+            const uint8_t *const xsrc = (K::EARLY && warp < NW / 2) ? smem + K::OFF_XLO : stile; // warp-uniform
 #pragma unroll
-            for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = stile + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
+            for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = xsrc + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
             static_for<R>([&](auto bi) {
                 constexpr int bb = decltype(bi)::value;
                 v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(s_sw[bb & SW] + (bb & ~SW) * PITCH);
             });
         }
         __syncwarp();
-        if constexpr (K::STAGE_SEPARATE) {
+        if constexpr (K::EARLY) {
+            if (warp < NW / 2) {
+                if (lane == 0) mbar_arrive(&lobar); // the lower exchange buffer may take staged rows
+            } else if (has_next) {
+                issue_tile(nvp, nt); // rows 512.. of the tile buffer (exchanged in place) are in registers
+            }
+        } else if constexpr (K::STAGE_SEPARATE) {
             if (has_next) issue_tile(nvp, nt); // the warp's region is in registers: fetch its share of the next tile
             // (a TMA L2 prefetch of the tile after next, cp.async.bulk.prefetch.tensor, was measured: +0.5 % on
             // 1024 x 512, -12 % on 4096 x 1024 — the wait for a tile is transfer time under a busy HBM, not DRAM latency)
@@ -413,6 +458,10 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         // ================= fold: stages 03-08 in energy form =================
         // output kb of (c, ka) is gate Q (ka + 32 kb) + sub, column col.  PHASES rounds: stage 32 of the warp's
         // output rows as [gate][T columns], every lane reads one whole row back and updates the gate's seven sums.
+        if constexpr (K::EARLY) { // staging goes into the lower exchange buffer: warps 0-3 must have read it
+            mbar_wait(&lobar, lophase);
+            lophase ^= 1;
+        }
         static_for<K::PHASES>([&](auto hi_) {
             constexpr int h = decltype(hi_)::value;
             static_for<K::KB_PHASE>([&](auto ki) {
@@ -474,7 +523,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             }
             __syncwarp();
         });
-        if constexpr (WIRE) {
+        if constexpr (WIRE || K::EARLY) {
             if (lane == 0) mbar_arrive(&ebar);
         }
 
@@ -573,6 +622,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             }
         }
         first = false;
+        ++n_tile;
         t = nt;
         vp = nvp;
     }
