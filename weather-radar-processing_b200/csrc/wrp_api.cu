@@ -206,15 +206,16 @@ static int create_impl(wrp_handle *h)
             const double kTwoPi = 6.283185307179586476925286766559;
             for (int tt = 0; tt < NT; tt++)
                 for (int m = 1; m <= 2; m++) {
-                    const double a = -kTwoPi * (double)(((long long)T * tt * m) % N) / N;
+                    // e^{-2 pi i m (T tt + (T-1)/2) / N}: first column of the tile, times the centring factor of the pairing
+                    const double a = -kTwoPi * m * ((double)(((long long)T * tt) % N) + 0.5 * (T - 1)) / N;
                     ttw[4 * (size_t)tt + 2 * (m - 1)] = (float)std::cos(a);
                     ttw[4 * (size_t)tt + 2 * (m - 1) + 1] = (float)std::sin(a);
                 }
             CK(h, upload(&h->fused.tile_tw, ttw.data(), ttw.size() * 4));
             for (int m = 1; m <= 2; m++)
-                for (int cc = 0; cc < 8; cc++) {
-                    const double a = -kTwoPi * (double)(cc * m) / N, sg = (cc & 1) ? -1.0 : 1.0;
-                    h->wcol[m - 1][cc] = make_float2((float)(sg * std::cos(a)), (float)(sg * std::sin(a)));
+                for (int cc = 0; cc < 8; cc++) { // pair (cc, T-1-cc), cc < T/2 (the rest is unused)
+                    const double phi = kTwoPi * m * (0.5 * (T - 1) - cc) / N, sg = (cc & 1) ? -1.0 : 1.0;
+                    h->wcol[m - 1][cc] = make_float2((float)(sg * std::cos(phi)), (float)(sg * std::sin(phi)));
                 }
             const size_t scratch_floats =
                 h->wire3 ? wrp::wire3_scratch_floats(h->stream_max_grid) : wrp::stream_scratch_floats(M, h->stream_max_grid);

@@ -82,6 +82,61 @@ template <int Q, bool WIRE> struct Cfg {
     static_assert((Q == 1 ? 2 : 1) * (SMEM + 1024 + 64) <= 233472, "shared memory per SM");
 };
 
+
+// One staged row of T columns x[0..T) (already scaled by wd(j)) folded into a gate's seven sums.
+//   E += sum |x_c|^2,  Y_0 += sum x_c,  Y_m += tw_m * S_m  with  S_m = sum_c (-1)^c e^{-i theta_m c} x_c.
+// Columns are paired around the tile's centre: with P = x_c + x_{T-1-c}, D = x_c - x_{T-1-c},
+//   (-1)^c e^{-i theta c} x_c + (-1)^{T-1-c} e^{-i theta (T-1-c)} x_{T-1-c}
+//       = e^{-i theta (T-1)/2} (-1)^c [cos(phi) D + i sin(phi) P],   phi = theta ((T-1)/2 - c),
+// so a pair costs four real FMAs per bin instead of eight, and the common factor lives in tile_tw.
+// kp[m][c] = ((-1)^c cos(phi_{m,c}), (-1)^c sin(phi_{m,c})) comes from the kernel's constant bank.
+template <int T>
+__device__ __forceinline__ void fold_row(const float2 (&x)[T], const float2 (&kp)[2][8], const float4 ttw, float (&a7)[7])
+{
+    float2 e2 = cmul2(x[0], x[0]);
+    static_for<T - 1>([&](auto ci) {
+        constexpr int cc = decltype(ci)::value + 1;
+        e2 = cfma2(x[cc], x[cc], e2);
+    });
+    float2 P[T / 2], D[T / 2];
+    static_for<T / 2>([&](auto pi) {
+        constexpr int q = decltype(pi)::value;
+        P[q] = cadd(x[q], x[T - 1 - q]);
+        D[q] = csub(x[q], x[T - 1 - q]);
+    });
+    float2 s0 = P[0];
+    static_for<T / 2 - 1>([&](auto pi) {
+        constexpr int q = decltype(pi)::value + 1;
+        s0 = cadd(s0, P[q]);
+    });
+    float2 s[2];
+    static_for<2>([&](auto mi) {
+        constexpr int m = decltype(mi)::value;
+        float sx = kp[m][0].x * D[0].x, sy = kp[m][0].x * D[0].y;
+        sx = fmaf(-kp[m][0].y, P[0].y, sx);
+        sy = fmaf(kp[m][0].y, P[0].x, sy);
+        static_for<T / 2 - 1>([&](auto pi) {
+            constexpr int q = decltype(pi)::value + 1;
+            sx = fmaf(kp[m][q].x, D[q].x, sx);
+            sx = fmaf(-kp[m][q].y, P[q].y, sx);
+            sy = fmaf(kp[m][q].x, D[q].y, sy);
+            sy = fmaf(kp[m][q].y, P[q].x, sy);
+        });
+        s[m] = make_float2(sx, sy);
+    });
+    a7[0] += e2.x + e2.y;
+    a7[1] += s0.x;
+    a7[2] += s0.y;
+    a7[3] = fmaf(s[0].x, ttw.x, a7[3]);
+    a7[3] = fmaf(-s[0].y, ttw.y, a7[3]);
+    a7[4] = fmaf(s[0].x, ttw.y, a7[4]);
+    a7[4] = fmaf(s[0].y, ttw.x, a7[4]);
+    a7[5] = fmaf(s[1].x, ttw.z, a7[5]);
+    a7[5] = fmaf(-s[1].y, ttw.w, a7[5]);
+    a7[6] = fmaf(s[1].x, ttw.w, a7[6]);
+    a7[6] = fmaf(s[1].y, ttw.z, a7[6]);
+}
+
 // ---- tile loads ------------------------------------------------------------------------------
 // planar: TMA.  The warp's own 8 KiB region of the tile (rows [8192/PITCH * warp, ...)) is one box
 // {T columns x 8192/PITCH rows} of the batch viewed as a [planes * M][N] matrix of 8-byte elements:
@@ -264,9 +319,9 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         const int col0 = t * T, col = col0 + c;
         uint8_t *const stile = xbuf + sub * (1024 * PITCH);
         float wdj = 0.f;
-        float2 wdp = make_float2(0.f, 0.f);
         if constexpr (Q == 1) wdj = __ldg(p.wd + col);
-        else wdp = __ldg(reinterpret_cast<const float2 *>(p.wd + col0) + tid % (T / 2));
+        float2 wdp = make_float2(0.f, 0.f);
+        if constexpr (Q == 4) wdp = __ldg(reinterpret_cast<const float2 *>(p.wd + col0) + tid % (T / 2));
 
         // M = 4096: the 16 window values of this thread's pre-pass units (the same for every tile), fetched
         // from global memory while the tile is still in flight
@@ -369,6 +424,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     constexpr int e = decltype(ei)::value;
                     constexpr int sa = brev<R>(4 * q + e); // even slot; partner row a + R/2 sits in sa + 1
                     static_assert(brev<R>(4 * q + e + R / 2) == sa + 1, "span-1 partner");
+                    // (wd(j) applied once to the 16 pass-2 outputs instead — 16 packed products for 32 scalar ones —
+                    // was measured 1.5 % SLOWER: it lengthens the chain between the transform and the fold)
                     const float wl = lo[e] * wdj, wh = hi[e] * wdj;
                     const float2 tt = cmul2(v[sa + 1], make_float2(wh, wh));
                     const float2 s2 = cfma2(v[sa], make_float2(wl, wl), tt); // A*wl + B*wh
@@ -478,22 +535,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     x[2 * q] = make_float2(w.x, w.y);
                     x[2 * q + 1] = make_float2(w.z, w.w);
                 });
-                float2 e2 = cmul2(x[0], x[0]);
-                float2 s0 = x[0], s1 = x[0], s2 = x[0];
-                static_for<T - 1>([&](auto ci) {
-                    constexpr int cc = decltype(ci)::value + 1;
-                    e2 = cfma2(x[cc], x[cc], e2);
-                    s0 = cadd(s0, x[cc]);
-                    const float2 w1 = p.wcol[0][cc], w2 = p.wcol[1][cc];
-                    s1.x = fmaf(x[cc].x, w1.x, s1.x);
-                    s1.x = fmaf(-x[cc].y, w1.y, s1.x);
-                    s1.y = fmaf(x[cc].x, w1.y, s1.y);
-                    s1.y = fmaf(x[cc].y, w1.x, s1.y);
-                    s2.x = fmaf(x[cc].x, w2.x, s2.x);
-                    s2.x = fmaf(-x[cc].y, w2.y, s2.x);
-                    s2.y = fmaf(x[cc].x, w2.y, s2.y);
-                    s2.y = fmaf(x[cc].y, w2.x, s2.y);
-                });
                 float a7[7];
                 if constexpr (K::ACC_SMEM) {
                     const float4 lo = acc_s[(slot * 2 + 0) * THREADS], hi4 = acc_s[(slot * 2 + 1) * THREADS];
@@ -502,17 +543,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
 #pragma unroll
                     for (int q = 0; q < 7; ++q) a7[q] = acc[slot][q];
                 }
-                a7[0] += e2.x + e2.y;
-                a7[1] += s0.x;
-                a7[2] += s0.y;
-                a7[3] = fmaf(s1.x, ttw.x, a7[3]);
-                a7[3] = fmaf(-s1.y, ttw.y, a7[3]);
-                a7[4] = fmaf(s1.x, ttw.y, a7[4]);
-                a7[4] = fmaf(s1.y, ttw.x, a7[4]);
-                a7[5] = fmaf(s2.x, ttw.z, a7[5]);
-                a7[5] = fmaf(-s2.y, ttw.w, a7[5]);
-                a7[6] = fmaf(s2.x, ttw.w, a7[6]);
-                a7[6] = fmaf(s2.y, ttw.z, a7[6]);
+                fold_row<T>(x, p.wcol, ttw, a7);
                 if constexpr (K::ACC_SMEM) {
                     acc_s[(slot * 2 + 0) * THREADS] = make_float4(a7[0], a7[1], a7[2], a7[3]);
                     acc_s[(slot * 2 + 1) * THREADS] = make_float4(a7[4], a7[5], a7[6], 0.f);
@@ -818,33 +849,7 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
                     x[2 * q] = make_float2(w.x, w.y);
                     x[2 * q + 1] = make_float2(w.z, w.w);
                 });
-                float2 e2 = cmul2(x[0], x[0]);
-                float2 s0 = x[0], s1 = x[0], s2 = x[0];
-                static_for<3>([&](auto ci) {
-                    constexpr int cc = decltype(ci)::value + 1;
-                    e2 = cfma2(x[cc], x[cc], e2);
-                    s0 = cadd(s0, x[cc]);
-                    const float2 w1 = p.wcol[0][cc], w2 = p.wcol[1][cc];
-                    s1.x = fmaf(x[cc].x, w1.x, s1.x);
-                    s1.x = fmaf(-x[cc].y, w1.y, s1.x);
-                    s1.y = fmaf(x[cc].x, w1.y, s1.y);
-                    s1.y = fmaf(x[cc].y, w1.x, s1.y);
-                    s2.x = fmaf(x[cc].x, w2.x, s2.x);
-                    s2.x = fmaf(-x[cc].y, w2.y, s2.x);
-                    s2.y = fmaf(x[cc].x, w2.y, s2.y);
-                    s2.y = fmaf(x[cc].y, w2.x, s2.y);
-                });
-                acc[h][0] += e2.x + e2.y;
-                acc[h][1] += s0.x;
-                acc[h][2] += s0.y;
-                acc[h][3] = fmaf(s1.x, ttw.x, acc[h][3]);
-                acc[h][3] = fmaf(-s1.y, ttw.y, acc[h][3]);
-                acc[h][4] = fmaf(s1.x, ttw.y, acc[h][4]);
-                acc[h][4] = fmaf(s1.y, ttw.x, acc[h][4]);
-                acc[h][5] = fmaf(s2.x, ttw.z, acc[h][5]);
-                acc[h][5] = fmaf(-s2.y, ttw.w, acc[h][5]);
-                acc[h][6] = fmaf(s2.x, ttw.w, acc[h][6]);
-                acc[h][6] = fmaf(s2.y, ttw.z, acc[h][6]);
+                fold_row<4>(x, p.wcol, ttw, acc[h]);
             }
             __syncwarp();
         });

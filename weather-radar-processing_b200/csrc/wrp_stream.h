@@ -18,7 +18,8 @@ struct StreamParams {
     const float *wd;        // [N] Doppler window wd(j)
     const float *wr4;       // M = 4096: wr(i) * c, natural order
     const float2 *tw4;      // M = 4096: exp(-2 pi i r / 4096), r < 1024 (radix-4 pre-pass)
-    const float4 *tile_tw;  // [N / T] (cos, sin) of -2 pi T t m / N for m = 1 and m = 2: a tile's factor of the clipped bins
+    const float4 *tile_tw;  // [N / T] (cos, sin) of -2 pi (T t + (T-1)/2) m / N for m = 1 and m = 2: a tile's factor of the
+                            // clipped bins (its first column's phase times the centring factor of the column pairing)
     // data
     const void *in;         // planar [S][C][M][N] float2, or wire records [S][M][N] x 12 B
     float *out;             // [S][M/2][2]  (ZdB, ZDR)
@@ -32,7 +33,8 @@ struct StreamParams {
     int chan_groups;        // 1: CTAs split the [plane][tile] space; C: CTA x works on channel x % C of the
                             // [sector][tile] space, so the C CTAs that read the same wire records run side by side
     float n_float, range_res, calib, taps_sum;
-    float2 wcol[2][8];      // (-1)^c exp(-2 pi i c m / N), m = 1, 2: column c's factor of clipped bin N/2 - m inside a tile
+    float2 wcol[2][8];      // [m][c], c < T/2: (-1)^c (cos, sin)(2 pi m ((T-1)/2 - c) / N): the pair (c, T-1-c)'s factors of
+                            // clipped bin N/2 - m (fold_row in wrp_stream.cu)
 };
 
 bool stream_supported(int M, int N, int wire);
