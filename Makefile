@@ -44,7 +44,13 @@ $(LIB): $(OBJS)
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
+# Checked build of the streaming kernels (WRP_CHECK range checks that trap): run the GPU tests against it with
+#   WRP_LIB=$$PWD/tools/libwrp_checked.so python -m pytest tests -m gpu
+checked: $(LIB)
+	$(NVCC) $(NVFLAGS) -DWRP_CHECKED -c $(CSRC)/wrp_stream.cu -o $(CSRC)/wrp_stream_checked.o
+	$(NVCC) $(ARCH) -shared -o tools/libwrp_checked.so $(filter-out $(CSRC)/wrp_stream.o,$(OBJS)) $(CSRC)/wrp_stream_checked.o -cudart static
+
 clean:
 	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(HOSTBINS)
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean checked

@@ -679,3 +679,69 @@ def test_volume_scan_through_the_c_abi_two_shards(wrp, sectors, refs):
         vol3 = vs3.process(wire)
     for k in range(S * E):
         assert_same_products(vol3[k], vol[k], f"3 shards vs 2, unit {k}")
+
+
+def test_misaligned_device_batch_is_an_error_not_a_fault(wrp, sectors):
+    """The streaming kernels fetch tiles by TMA, whose tensor map needs a 16-byte-aligned base: a batch at an odd
+    8-byte offset must come back as a status with a message (no launch, no fault), and the handle stays usable."""
+    torch = pytest.importorskip("torch")
+    x = wrp.synth.to_planar(sectors[0])
+    buf = torch.zeros(x.size * 2 + 4, dtype=torch.float32, device="cuda")
+    buf[2:2 + x.size * 2] = torch.from_numpy(x.view(np.float32).reshape(-1)).cuda()
+    out = torch.zeros((1, M // 2, 2), device="cuda")
+    with wrp.RadarChain(0) as ch:
+        with pytest.raises(wrp.WrpError) as e:
+            ch.process_device(buf.data_ptr() + 8, 1, out.data_ptr(), 0)
+        assert "aligned" in str(e.value)
+        good = torch.from_numpy(x.view(np.float32).reshape(-1)).cuda()
+        ch.process_device(good.data_ptr(), 1, out.data_ptr(), 0)
+        torch.cuda.synchronize()
+    assert np.isfinite(out.cpu().numpy()[0, 1:]).all()
+
+
+@pytest.mark.parametrize("n,c,fmt", [(2048, 1, "planar"), (64, 3, "wire"), (256, 2, "wire")])
+def test_stream_kernels_other_doppler_lengths(wrp, oracle, n, c, fmt):
+    """The streaming kernels take any power-of-two Doppler length N >= 64 (N only sets the number of tiles per
+    plane and the clipped bins' phase tables): a long dwell, the shortest one, and a two-channel wire sector."""
+    iq = wrp.synth.make_sector_int16(M, n, 3, 1)
+    ref = oracle.chain(wrp.synth.to_planar(iq, c).astype(np.complex128))
+    data = wrp.synth.to_planar(iq, c)[None] if fmt == "planar" else wrp.synth.to_wire(iq)[None]
+    kw = {} if fmt == "planar" else {"input_fmt": wrp.FMT_WIRE_I16BE}
+    with wrp.RadarChain(0, n_cols_N=n, n_channels=c, max_batch=1, **kw) as ch:
+        assert ch.chain_kernel in ("chain_stream_kernel", "chain_wire3_kernel")
+        out = ch.process_host(data, 1)[0]
+    if c == 1:
+        assert np.all(out[:, 1] == 0)
+        assert np.isneginf(out[0, 0]) and np.max(np.abs(out[1:, 0] - ref.zdb[1:])) <= DB_TOL
+    else:
+        assert_products_close(out, ref.zdb, ref.zdr, f"N={n} C={c} {fmt}")
+
+
+@pytest.mark.parametrize("fmt,S,reps", [("planar", 40, 300), ("planar", 143, 120), ("wire", 40, 200)])
+def test_run_to_run_determinism_stress(wrp, sectors, fmt, S, reps):
+    """Hundreds of launches of the same resident batch must be bit-identical.  This is the regression test of a
+    real race found in round 2: a TMA copy of the next tile issued right after the ISSUE of the pass-2 shared-memory
+    loads of a warp's region could land before those loads had returned (visible as garbage in the first rows of the
+    region, a few launches in a hundred).  The copy — and every mbarrier arrive that releases a region being read —
+    is now data-dependent on the completion of the loads (tma_load_2d / mbar_arrive_after)."""
+    torch = pytest.importorskip("torch")
+    if fmt == "planar":
+        base = np.stack([wrp.synth.to_planar(x) for x in sectors])
+        kw = {}
+    else:
+        base = np.stack([wrp.synth.to_wire(x) for x in sectors])
+        kw = {"input_fmt": wrp.FMT_WIRE_I16BE}
+    host = np.stack([base[i % 3] for i in range(S)])
+    x = torch.from_numpy(host.view(np.uint8).reshape(-1)).cuda()
+    out = torch.empty((S, M // 2, 2), dtype=torch.float32, device="cuda")
+    with wrp.RadarChain(0, max_batch=8, **kw) as ch:
+        ch.process_device(x.data_ptr(), S, out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        ref = out.clone()
+        bad = 0
+        for _ in range(reps):
+            out.zero_()
+            ch.process_device(x.data_ptr(), S, out.data_ptr(), 0)
+            torch.cuda.synchronize()
+            bad += int(not torch.equal(out.view(torch.int32), ref.view(torch.int32)))
+    assert bad == 0, f"{bad} of {reps} launches differ from the first"

@@ -145,6 +145,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
+// mbarrier arrive that releases a shared-memory region the warp has been READING: `dep_and_zero` = (a value derived
+// from the last of those loads) AND (a kernel parameter that is always 0).  Added to the barrier address it changes
+// nothing but keeps the arrive behind the COMPLETION of the loads in the SASS, not merely behind their issue.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t dep_and_zero)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + dep_and_zero) : "memory");
+}
+
 // cp.async groups: the calling thread's copies since its previous commit form one group
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait_group()

@@ -36,6 +36,20 @@
 namespace wrp {
 namespace stream {
 
+// Checked build (make checked -> tools/libwrp_checked.so, -DWRP_CHECKED): every index a kernel of this file uses
+// for a global store, and every tile / plane / sector it derives from its work partition, is range-checked and a
+// violation traps (-> cudaErrorLaunchFailure -> WRP_ERR_CUDA).  compute-sanitizer is closed on the measurement pool,
+// so this is how the GPU tests double as a memory-safety run (profiles/r02_checked_build.txt).  No code in a
+// normal build.
+#ifdef WRP_CHECKED
+#define WRP_CHECK(cond)                                                                                              \
+    do {                                                                                                             \
+        if (!(cond)) __trap();                                                                                       \
+    } while (0)
+#else
+#define WRP_CHECK(cond) ((void)0)
+#endif
+
 constexpr int R = 32;
 constexpr int WRC_ROW = 32 * 4 + 16; // wr(i)*c transposed [32 b][32 a] floats, rows padded by 16 B
 constexpr int TWA_ROW = 32 * 8 + 16; // range inter-pass twiddles [32 b][32 ka] float2
@@ -59,18 +73,12 @@ template <int Q, bool WIRE> struct Cfg {
     // planar: a separate staging buffer, because the warp's region of the exchange buffer is already
     // receiving the next tile; wire: the region itself (the next tile lands in the landing buffer)
     static constexpr bool STAGE_SEPARATE = !WIRE;
-    // planar M = 1024: the lower half of the exchange (ka < 16) goes to its own 32 KiB buffer, so rows 0..511 of
-    // the tile buffer are dead after the pass-1 reads and are requested again right then (58 % of a tile's work
-    // earlier than the upper half, which is exchanged in place); the fold stages inside that buffer
-    static constexpr bool EARLY = Q == 1 && !WIRE;
-    static constexpr int XLO = EARLY ? 512 * PITCH : 0;
-    static constexpr int STAGE = (STAGE_SEPARATE && !EARLY) ? NW * ROWS_PHASE * PITCH : 0;
+    static constexpr int STAGE = STAGE_SEPARATE ? NW * ROWS_PHASE * PITCH : 0;
     static constexpr int RPT = PHASES;            // gates per thread: 2 (M = 1024) or 4 (M = 4096)
     static constexpr bool ACC_SMEM = Q == 4;
     static constexpr int ACC = ACC_SMEM ? RPT * 2 * THREADS * 16 : 0; // [gate slot][chunk][thread] float4
     static constexpr int OFF_LAND = XBUF;
-    static constexpr int OFF_XLO = OFF_LAND + LAND;
-    static constexpr int OFF_STAGE = OFF_XLO + XLO;
+    static constexpr int OFF_STAGE = OFF_LAND + LAND;
     static constexpr int OFF_ACC = OFF_STAGE + STAGE;
     static constexpr int OFF_TAB = OFF_ACC + ACC;
     static constexpr int OFF_WRC = OFF_TAB;                      // Q = 1
@@ -147,22 +155,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+// `after_and_zero`: (a register produced by the LAST shared-memory load the issuing thread made from the destination
+// buffer) AND (StreamParams::zero, a kernel parameter that is always 0 but that ptxas cannot know).  Added to the row
+// coordinate it changes nothing and makes the copy data-dependent on that load in the SASS, so it cannot issue before
+// the loads of the old tile have returned (loads of one warp return in order).  Without it the copy is only ordered
+// behind the ISSUE of those loads — and a box that hits L2 can overtake loads queued in a busy LSU and overwrite the
+// rows they are about to read (seen as run-to-run differences in the first rows of a warp's region of the tile).
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                            uint32_t after_and_zero = 0)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                      smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1 + (int)after_and_zero)
                  : "memory");
 }
 template <int Q, bool WIRE>
 __device__ __forceinline__ void issue_tile_planar(const CUtensorMap *tmap, uint8_t *xbuf, uint64_t *bar, int plane, int t,
-                                                  int warp, int lane)
+                                                  int warp, int lane, uint32_t after)
 {
     using K = Cfg<Q, WIRE>;
     constexpr int RPWARP = 8192 / K::PITCH;
     if (lane == 0) {
         mbar_expect_tx(bar, 8192);
-        tma_load_2d(xbuf + warp * 8192, tmap, t * K::T, plane * (1024 * Q) + warp * RPWARP, bar);
+        tma_load_2d(xbuf + warp * 8192, tmap, t * K::T, plane * (1024 * Q) + warp * RPWARP, bar, after);
     }
 }
 // wire: every thread fetches 32 of the tile's 8192 (I, Q) pairs — 4 bytes at offset 4 ch of the
@@ -196,9 +211,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar; // the next tile has landed: planar — one arrival + 8 KiB of TMA bytes per warp;
                                            // wire — one arrival per thread, fired by its cp.asyncs
-    __shared__ __align__(8) uint64_t ebar; // wire / early: every warp is done with its staged rows of the previous tile
-    __shared__ __align__(8) uint64_t lobar; // early: warps 0-3 have read their pass-2 operands out of the lower exchange buffer
-    __shared__ int s_flag, s_rdcnt;
+    __shared__ __align__(8) uint64_t ebar; // wire: every warp is done with its staged rows of the previous tile
+    __shared__ int s_flag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *const xbuf = smem;
@@ -235,44 +249,30 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         }
     }
     if (tid == 0) {
-        mbar_init(&mbar, WIRE ? THREADS : (K::EARLY ? NW / 2 + 1 : NW));
+        mbar_init(&mbar, WIRE ? THREADS : NW);
         mbar_init(&ebar, NW);
-        mbar_init(&lobar, NW / 2);
-        s_rdcnt = 0;
     }
     __syncthreads();
 
     int vp = g_lo / p.NT, t = g_lo - vp * p.NT; // virtual plane and tile of the current item
     const int vp_lo = vp;
-    auto issue_tile = [&](int vplane, int tile) {
+    auto issue_tile = [&](int vplane, int tile, uint32_t after = 0) {
         const int plane = real_plane(vplane);
         if constexpr (WIRE) {
             const int sector = plane / p.C;
             issue_tile_wire(p, smem + K::OFF_LAND, &mbar, sector, plane - sector * p.C, tile, tid);
         } else {
-            issue_tile_planar<Q, WIRE>(&tmap, xbuf, &mbar, plane, tile, warp, lane);
+            issue_tile_planar<Q, WIRE>(&tmap, xbuf, &mbar, plane, tile, warp, lane, after);
         }
     };
-    if constexpr (K::EARLY) { // same arrival pattern as every later tile: one for rows 0..511, one per warp 4-7
-        if (warp >= NW / 2) {
-            issue_tile(vp, t);
-        } else if (tid == 0) {
-            mbar_expect_tx(&mbar, 4 * 8192);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) tma_load_2d(xbuf + q * 8192, &tmap, t * T, real_plane(vp) * 1024 + q * 128, &mbar);
-        }
-    } else {
-        issue_tile(vp, t);
-    }
+    issue_tile(vp, t);
 
     // ---- per-thread constants of the fold ---------------------------------------------------------
     // writer: thread (column c, ka_l) stores output kb of the phase at staged row R = kbl * KPW + ka_l;
     // 16-byte chunk (c >> 1) of a row is XOR-swizzled with s(R) so that the 128-bit row reads below are
     // conflict-free: s(R) = (R >> 1) & 3 for 64-byte rows, (R >> 2) & 1 for 32-byte rows
     const int cw = lane % T, ka_l = lane / T;
-    uint8_t *const stage = K::EARLY            ? smem + K::OFF_XLO + warp * (K::ROWS_PHASE * PITCH)
-                           : K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH)
-                                               : xbuf + warp * 8192;
+    uint8_t *const stage = K::STAGE_SEPARATE ? smem + K::OFF_STAGE + warp * (K::ROWS_PHASE * PITCH) : xbuf + warp * 8192;
     uint8_t *wbase[2]; // by parity of kbl (T = 8: s depends on it; T = 4: both entries equal)
     static_assert(T == 8 || (KPW * 4) % 8 == 0, "T = 4: s(R) = (R >> 2) & 1 must not depend on kbl");
 #pragma unroll
@@ -302,15 +302,15 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
     }
     float4 *const acc_s = reinterpret_cast<float4 *>(smem + K::OFF_ACC) + tid; // [slot][chunk][thread]
 
-    uint32_t phase = 0, ephase = 0, lophase = 0;
+    uint32_t phase = 0, ephase = 0;
     bool first = true;
-    int n_tile = 0; // tiles this CTA has started
 
     for (int g = g_lo; g < g_end; ++g) {
         int nt = t + 1, nvp = vp;
         if (nt == p.NT) nt = 0, ++nvp;
         const bool has_next = g + 1 < g_end;
         const int plane = real_plane(vp);
+        WRP_CHECK(t >= 0 && t < p.NT && plane >= 0 && plane < p.S * p.C && g >= 0 && g < total);
         const float4 ttw = __ldg(p.tile_tw + t); // this tile's factors of the two clipped bins
 
         // thread -> (sub-tile, column, b): Q = 4: thread group `sub` (32 T threads) owns the 1024-row sub-tile k0 = sub
@@ -398,19 +398,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                 v[brev<R>(a)] = *reinterpret_cast<const float2 *>(src + a * (R * PITCH));
             });
         }
-        if constexpr (K::EARLY) {
-            // the last warp to have read the tile requests rows 0..511 of the next one (the regions of warps 0-3)
-            __syncwarp();
-            if (lane == 0) {
-                const int old = atomicAdd(&s_rdcnt, 1);
-                if (old == NW * n_tile + NW - 1 && has_next) {
-                    mbar_expect_tx(&mbar, 4 * 8192);
-                    const int np = real_plane(nvp);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tma_load_2d(xbuf + q * 8192, &tmap, nt * T, np * 1024 + q * 128, &mbar);
-                }
-            }
-        }
         if constexpr (Q == 1) {
             // stage 01 (x *= wr(i)*c*wd(j), rpv2.cu:86-91) fused into the first butterfly stage: the span-1
             // partners of the bit-reversed network are rows a and a + 16
@@ -437,8 +424,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         } else {
             fft_dit<R, -1>(v);
         }
-        if constexpr (WIRE || K::EARLY) {
-            // the (lower) exchange buffer doubles as the fold's staging area: wait until every warp has read its
+        if constexpr (WIRE) {
+            // the exchange buffer doubles as the fold's staging area: wait until every warp has read its
             // staged rows of the previous tile back before overwriting them
             if (!first) {
                 mbar_wait(&ebar, ephase);
@@ -452,8 +439,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             uint8_t *d_sw[SW + 1];
 #pragma unroll
             for (int sx = 0; sx <= SW; ++sx) d_sw[sx] = stile + (b ^ sx) * PITCH + c * 8;
-            // early: rows 32 ka + .. with ka < 16 live in the lower exchange buffer (same row map)
-            const ptrdiff_t lo_shift = K::EARLY ? (smem + K::OFF_XLO) - stile : 0;
             float4 wq[3] = {t4[0], t4[1], t4[2]};
             static_for<R / 2>([&](auto qi) {
                 constexpr int q = decltype(qi)::value;
@@ -461,9 +446,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                 if constexpr (q + 3 < R / 2) wq[q % 3] = t4[q + 3];
                 const float2 y0 = q == 0 ? v[0] : cmul(v[2 * q], make_float2(w.x, w.y));
                 const float2 y1 = cmul(v[2 * q + 1], make_float2(w.z, w.w));
-                constexpr bool lo = K::EARLY && 2 * q + 1 < 16;
-                *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH) + (lo ? lo_shift : 0)) = y0;
-                *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH) + (lo ? lo_shift : 0)) = y1;
+                *reinterpret_cast<float2 *>(d_sw[(2 * q) & SW] + (2 * q) * (R * PITCH)) = y0;
+                *reinterpret_cast<float2 *>(d_sw[(2 * q + 1) & SW] + (2 * q + 1) * (R * PITCH)) = y1;
             });
         }
         // the exchange: the one barrier of a 1024-point column group
@@ -483,28 +467,28 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         const int ka = b; // rows 32 ka + .. of warp w are its own 8 KiB region
         {
             const uint8_t *s_sw[SW + 1];
-            const uint8_t *const xsrc = (K::EARLY && warp < NW / 2) ? smem + K::OFF_XLO : stile; // warp-uniform
 #pragma unroll
-            for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = xsrc + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
+            for (int sx = 0; sx <= SW; ++sx) s_sw[sx] = stile + ka * (R * PITCH) + c * 8 + ((ka ^ sx) & SW) * PITCH;
             static_for<R>([&](auto bi) {
                 constexpr int bb = decltype(bi)::value;
                 v[brev<R>(bb)] = *reinterpret_cast<const float2 *>(s_sw[bb & SW] + (bb & ~SW) * PITCH);
             });
         }
         __syncwarp();
-        if constexpr (K::EARLY) {
-            if (warp < NW / 2) {
-                if (lane == 0) mbar_arrive(&lobar); // the lower exchange buffer may take staged rows
-            } else if (has_next) {
-                issue_tile(nvp, nt); // rows 512.. of the tile buffer (exchanged in place) are in registers
+        // first butterfly stage: it consumes every loaded value, so what follows is ordered behind the COMPLETION of
+        // this warp's pass-2 reads (tma_load_2d / mbar_arrive_after explain why their issue is not enough)
+        dit_stage<R, 1, -1>(v);
+        {
+            const uint32_t dep = __float_as_uint(v[R - 1].x) & (uint32_t)p.zero;
+            if constexpr (K::STAGE_SEPARATE) {
+                if (has_next) issue_tile(nvp, nt, dep); // the warp's region is in registers: fetch its share of the next tile
+                // (a TMA L2 prefetch of the tile after next, cp.async.bulk.prefetch.tensor, was measured: +0.5 % on
+                // 1024 x 512, -12 % on 4096 x 1024 — the wait for a tile is transfer time under a busy HBM, not DRAM latency)
             }
-        } else if constexpr (K::STAGE_SEPARATE) {
-            if (has_next) issue_tile(nvp, nt); // the warp's region is in registers: fetch its share of the next tile
-            // (a TMA L2 prefetch of the tile after next, cp.async.bulk.prefetch.tensor, was measured: +0.5 % on
-            // 1024 x 512, -12 % on 4096 x 1024 — the wait for a tile is transfer time under a busy HBM, not DRAM latency)
         }
-        fft_dit<R, -1>(v);
+        fft_dit_after_stage1<R, -1>(v);
         if (p.x2_tap) { // debug tap (tests): stage 02 rows k < M/2 as the product kernel computes them
+            WRP_CHECK(plane >= 0 && plane < p.S * p.C && Q * ka + sub + Q * R * 15 < p.half_m && col >= 0 && col < p.N);
             float2 *o = p.x2_tap + ((size_t)plane * p.half_m + Q * ka + sub) * (size_t)p.N + col;
             static_for<R / 2>([&](auto ki) {
                 constexpr int kb = decltype(ki)::value;
@@ -515,10 +499,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         // ================= fold: stages 03-08 in energy form =================
         // output kb of (c, ka) is gate Q (ka + 32 kb) + sub, column col.  PHASES rounds: stage 32 of the warp's
         // output rows as [gate][T columns], every lane reads one whole row back and updates the gate's seven sums.
-        if constexpr (K::EARLY) { // staging goes into the lower exchange buffer: warps 0-3 must have read it
-            mbar_wait(&lobar, lophase);
-            lophase ^= 1;
-        }
         static_for<K::PHASES>([&](auto hi_) {
             constexpr int h = decltype(hi_)::value;
             static_for<K::KB_PHASE>([&](auto ki) {
@@ -554,8 +534,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             }
             __syncwarp();
         });
-        if constexpr (WIRE || K::EARLY) {
-            if (lane == 0) mbar_arrive(&ebar);
+        if constexpr (WIRE) { // behind the completion of the last read-back (its sums), not its issue
+            if (lane == 0) mbar_arrive_after(&ebar, __float_as_uint(acc[K::ACC_SMEM ? 0 : K::PHASES - 1][0]) & (uint32_t)p.zero);
         }
 
         // ================= end of the plane (or of this CTA's run): products =================
@@ -590,9 +570,11 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     const int k = slot_gate(r);
 #pragma unroll
                     for (int q = 0; q < 7; ++q) mine[q * hm + k] = vals[r][q];
+                    WRP_CHECK(k >= 0 && k < hm && blockIdx.x < gridDim.x);
                 }
                 __threadfence();
                 __syncthreads();
+                WRP_CHECK(plane >= 0 && plane < p.S * p.C);
                 if (tid == 0) s_flag = atomicAdd(p.plane_cnt + plane, 1);
                 __syncthreads();
                 const int x_first = cta_of(plane_first), x_last = cta_of(plane_first + p.NT - 1);
@@ -626,6 +608,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     for (int q = 2; q < 7; ++q) removed = fmaf(vals[r][q], vals[r][q], removed);
                     // stages 05-08: the row sum of the circular convolution is sum(taps) x the row sum
                     const float pw = fmaxf(fmaf(p.n_float, vals[r][0], -removed), 0.f) * p.taps_sum;
+                    WRP_CHECK(plane >= 0 && plane < p.S * p.C && k >= 0 && k < hm && sector >= 0 && sector < p.S);
                     p.power[(size_t)plane * hm + k] = pw;
                     if (p.C == 1) { // stage 09 only (rpv2.cu:199-213 with a single channel)
                         const float rg = (float)k * p.range_res;
@@ -653,7 +636,6 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
             }
         }
         first = false;
-        ++n_tile;
         t = nt;
         vp = nvp;
     }
@@ -759,6 +741,7 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
         // the other landing buffer was last read in pass 1 of the previous tile, and every thread has passed
         // that tile's exchange barrier: request the next tile now, a whole tile ahead
         if (tid == 0 && has_next) issue_raw(nsector, nt, buf ^ 1);
+        WRP_CHECK(t >= 0 && t < NT && sector >= 0 && sector < p.S && g < total);
         const float4 ttw = __ldg(p.tile_tw + t);
         const float wdj = __ldg(p.wd + t * RC + c2 / 3);
 
@@ -822,10 +805,12 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
             });
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(ebar);
-        fft_dit<R, -1>(v);
+        dit_stage<R, 1, -1>(v); // consumes every loaded value: the arrive below follows the completion of the reads
+        if (lane == 0) mbar_arrive_after(ebar, __float_as_uint(v[R - 1].x) & (uint32_t)p.zero);
+        fft_dit_after_stage1<R, -1>(v);
         const int col = t * RC + colw;
         if (p.x2_tap) {
+            WRP_CHECK(ka + R * 15 < hm && col >= 0 && col < p.N);
             float2 *o = p.x2_tap + ((size_t)(sector * 3 + ch) * hm + ka) * (size_t)p.N + col;
             static_for<R / 2>([&](auto ki) {
                 constexpr int kb = decltype(ki)::value;
@@ -906,6 +891,7 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
                     float removed = vals[r][1] * vals[r][1];
 #pragma unroll
                     for (int q = 2; q < 7; ++q) removed = fmaf(vals[r][q], vals[r][q], removed);
+                    WRP_CHECK(k >= 0 && k < hm && ch >= 0 && ch < 3);
                     p.power[((size_t)sector * 3 + ch) * hm + k] =
                         fmaxf(fmaf(p.n_float, vals[r][0], -removed), 0.f) * p.taps_sum;
                 }

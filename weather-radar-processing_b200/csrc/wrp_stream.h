@@ -32,6 +32,7 @@ struct StreamParams {
     int half_m;             // M / 2
     int chan_groups;        // 1: CTAs split the [plane][tile] space; C: CTA x works on channel x % C of the
                             // [sector][tile] space, so the C CTAs that read the same wire records run side by side
+    int zero;               // always 0; makes a TMA issue data-dependent on a loaded value (tma_load_2d)
     float n_float, range_res, calib, taps_sum;
     float2 wcol[2][8];      // [m][c], c < T/2: (-1)^c (cos, sin)(2 pi m ((T-1)/2 - c) / N): the pair (c, T-1-c)'s factors of
                             // clipped bin N/2 - m (fold_row in wrp_stream.cu)
