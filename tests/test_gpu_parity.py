@@ -631,10 +631,14 @@ def test_radar_processor_udp_loopback(wrp, sectors, refs):
         tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
         n_sec = 3
         for k in range(n_sec):
+            # UDP has no back-pressure and the reference's protocol no loss detection (read_single.cc:145-148): one
+            # datagram per sweep, paced at ~100 MB/s — the processor (device handle created before it reported
+            # "listening") drains far faster, so the socket buffer (rmem_max may be 4 MiB) never fills.  The loop is
+            # open: like the reference's, the processor reads sector k+1 before it collects sector k.
             wire = wrp.synth.to_wire(sectors[k]).reshape(M, N * 12)
-            for i in range(M):  # one datagram per sweep, paced so that the loopback queue never overflows
+            for i in range(M):
                 tx.sendto(wire[i].tobytes(), ("127.0.0.1", p_in))
-                if i % 64 == 63:
+                if i % 32 == 31:
                     time.sleep(0.002)
         for k in range(n_sec):
             zb, _ = rx[0].recvfrom(65536)

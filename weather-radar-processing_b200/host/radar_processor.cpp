@@ -110,12 +110,8 @@ void RadarProcessor::deliver(int sector, int elevation, const float *slot)
     ++processed_;
 }
 
-int RadarProcessor::start()
+static wrp_config processor_config(int n_sweeps, int n_samples, int n_cuda_streams, int batch)
 {
-    if (!source_) {
-        error_ = "start: no input (call set_comms or set_source first)";
-        return WRP_ERR_STATE;
-    }
     wrp_config cfg;
     wrp_default_config(&cfg);
     cfg.n_rows_M = n_sweeps;
@@ -123,13 +119,29 @@ int RadarProcessor::start()
     cfg.n_channels = 3;
     cfg.n_streams = n_cuda_streams < 2 ? 2 : n_cuda_streams;
     cfg.input_fmt = WRP_FMT_WIRE_I16BE;
-    cfg.max_batch = batch_;
-    if (!handle_) {
-        const int rc = wrp_create(&cfg, device_, &handle_);
-        if (rc != WRP_OK) {
-            error_ = wrp_last_error(nullptr);
-            return rc;
-        }
+    cfg.max_batch = batch;
+    return cfg;
+}
+
+int RadarProcessor::prepare()
+{
+    if (handle_) return WRP_OK;
+    const wrp_config cfg = processor_config(n_sweeps, n_samples, n_cuda_streams, batch_);
+    const int rc = wrp_create(&cfg, device_, &handle_);
+    if (rc != WRP_OK) error_ = wrp_last_error(nullptr);
+    return rc;
+}
+
+int RadarProcessor::start()
+{
+    if (!source_) {
+        error_ = "start: no input (call set_comms or set_source first)";
+        return WRP_ERR_STATE;
+    }
+    const wrp_config cfg = processor_config(n_sweeps, n_samples, n_cuda_streams, batch_);
+    {
+        const int rc = prepare();
+        if (rc != WRP_OK) return rc;
     }
     const size_t sector_bytes = (size_t)12 * n_sweeps * n_samples;
     const size_t slot_floats = (size_t)o_types * (n_sweeps / 2);

@@ -34,6 +34,9 @@ class RadarProcessor {
     // returns).  0 on success, a wrp_status otherwise (text in last_error()).
     int start();
     void set_comms(int in_port, int *out_ports, int out_length);
+    // extension: create the device handle now (start() does it lazily), so that a caller can announce readiness
+    // before the first datagram arrives — UDP has no back-pressure and a sector is a 6 MB burst
+    int prepare();
 
     // extensions
     void set_source(Source s) { source_ = std::move(s); }

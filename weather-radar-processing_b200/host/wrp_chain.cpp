@@ -80,6 +80,7 @@ int main(int argc, char **argv)
         if (!dst.empty()) proc.set_out_address(dst);
         proc.set_recv_timeout_ms(atoi(arg(argc, argv, "--udp-timeout-ms", "0")));
         proc.set_comms(udp_in, ports, 2);
+        if (proc.prepare()) return fprintf(stderr, "wrp_chain: %s\n", proc.last_error()), 3; // device handle before readiness
         printf("listening on udp %d\n", udp_in);
         fflush(stdout);
         const int rc = proc.start();
