@@ -608,7 +608,7 @@ def test_radar_processor_udp_loopback(wrp, sectors, refs):
     (read_single.cc:145-148) and its products come back as two 2 + 4*512-byte datagrams
     [sector BE16][512 BE floats] on the ZdB and ZDR ports (gpu_1fp_streamcasc.cu:709-725)."""
     import os, socket, subprocess, time
-    exe = os.path.join(os.path.dirname(wrp.LIB_PATH), "host", "wrp_chain")
+    exe = os.path.join(os.path.dirname(wrp.__file__), "host", "wrp_chain")  # (not next to WRP_LIB: that may be an A/B build)
     assert os.path.exists(exe), "build the host binaries first (make)"
 
     def free_port():
