@@ -419,6 +419,25 @@ def test_stress_shape_4096x1024_staged(wrp, oracle):
     assert_products_close(fused, out[:, 0].astype(np.float64), out[:, 1].astype(np.float64), "fused vs staged 4096x1024")
 
 
+@pytest.mark.parametrize("n,c", [(1024, 3), (512, 2)])
+def test_4096_range_gates_literal_doppler_transform(wrp, oracle, n, c):
+    """M = 4096 with doppler_form = WRP_DOPPLER_FFT: the two-kind queue kernel runs the literal mean removal, Doppler
+    transform, shift, clip and |.|^2 on the 4096-row shape (three-slot x2 ring, so tiles wait for ring slots and
+    Doppler blocks for tiles); products against the oracle and against the energy form of the streaming kernel."""
+    m, S = 4096, 4
+    secs = [wrp.synth.to_planar(wrp.synth.make_sector_int16(m, n, s, 0), c) for s in range(2)]
+    refs_ = [oracle.chain(x.astype(np.complex128)) for x in secs]
+    batch = np.stack([secs[i % 2] for i in range(S)])
+    with wrp.RadarChain(0, n_rows_M=m, n_cols_N=n, n_channels=c, max_batch=2, doppler_form=wrp.DOPPLER_FFT) as ch:
+        assert ch.chain_kernel == "chain_persistent_kernel"
+        lit = ch.process_host(batch, S)
+    with wrp.RadarChain(0, n_rows_M=m, n_cols_N=n, n_channels=c, max_batch=2) as ch:
+        energy = ch.process_host(batch, S)
+    for i in range(S):
+        assert_products_close(lit[i], refs_[i % 2].zdb, refs_[i % 2].zdr, f"literal 4096x{n}x{c} sector {i}")
+        assert_same_products(lit[i], energy[i], f"literal vs energy form, sector {i}", tol=2e-3)
+
+
 @pytest.mark.parametrize("n,c", [(1024, 3), (512, 2), (512, 3), (1024, 1)])
 def test_fused_path_4096_range_gates(wrp, oracle, n, c):
     """BASELINE config 5 (M = 4096) through the streaming kernel: radix-4 pre-pass + four 1024-point
