@@ -153,9 +153,12 @@ __device__ __forceinline__ void discard_l2_line(const void *p)
 //   Doppler block: the warp's RPW rows of the x2 ring, contiguous N*8 bytes each
 template <int N, int T, int Q>
 __device__ __forceinline__ void issue_warp_load(const Item &it, const PersistParams &p, uint8_t *tile, uint64_t *bar,
-                                                int warp, int lane)
+                                                int warp, int lane, uint32_t after_and_zero = 0)
 {
-    uint8_t *dst = tile + warp * 8192 + lane * 16;
+    // after_and_zero = (a value derived from the warp's LAST read of the region) & p.zero: always 0, but it makes the
+    // copies below data-dependent on the completion of those reads — cp.async data lands asynchronously, and being
+    // ordered behind the mere ISSUE of the loads is not enough (wrp_stream.cu, tma_load_2d, has the full story)
+    uint8_t *dst = tile + warp * 8192 + lane * 16 + after_and_zero;
     if (it.kind == 0) {
         constexpr int tiles_per_plane = N / T, CPR = T / 2, RPWARP = 1024 / T;
         const int ch = it.sub / tiles_per_plane, col_tile = it.sub - ch * tiles_per_plane;
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
         };
         // a warp that has pulled its last operand out of its region learns the next item and, if
         // that item's dependency is already met, starts fetching its own region of it
-        auto prefetch_next = [&]() {
+        auto prefetch_next = [&](uint32_t after_and_zero) {
             while (s_seq < n + 2) {
             }
             {
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 nit = Item{pub.x, pub.y, pub.z, pub.w};
             }
             if (nit.kind >= 0 && s_go >= n + 2) {
-                issue_warp_load<N, T, Q>(nit, p, tile, &mbar, warp, lane);
+                issue_warp_load<N, T, Q>(nit, p, tile, &mbar, warp, lane, after_and_zero);
                 loaded = true;
             }
         };
@@ -483,8 +486,9 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 });
             }
             __syncwarp();
-            prefetch_next();
-            fft_dit<R, -1>(v);
+            dit_stage<R, 1, -1>(v); // consumes every loaded value: the prefetch below follows the completion of the reads
+            prefetch_next(__float_as_uint(v[R - 1].x) & (uint32_t)p.zero);
+            fft_dit_after_stage1<R, -1>(v);
             {
                 // sub-transform output k' = ka + 32 kb < 512 is row Q k' + sub of the M-point transform
                 float2 *out =
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                         publish_next();
                         publish_pending();
                         __syncwarp();
-                        prefetch_next();
+                        prefetch_next(__float_as_uint(v[R1B - 1].x) & (uint32_t)p.zero);
                     }
 #endif
                     float2 e2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                 publish_next();
                 publish_pending();
                 __syncwarp();
-                prefetch_next();
+                prefetch_next(__float_as_uint(q[RPW - 1][0]) & (uint32_t)p.zero);
 #endif
                 // lane sums: with two rows per warp the first exchange also transposes, so the low
                 // half-warp ends up with row 0 (hh) and the high one with row 1 (vv)
@@ -666,8 +670,9 @@ __global__ void __launch_bounds__(32 * T * Q, 16 / (T * Q))
                     });
                 }
                 __syncwarp();
-                prefetch_next();
-                fft_dit<32, +1>(u);
+                dit_stage<32, 1, +1>(u); // consumes every loaded value (see the range tile)
+                prefetch_next(__float_as_uint(u[31].x) & (uint32_t)p.zero);
+                fft_dit_after_stage1<32, +1>(u);
                 // stage 03 shift + clip (rpv2.cu:137-148): the zeroed columns N-1, N-2 are bins N/2-1 =
                 // (R1B-1) + R1B*15 and N/2-2; stage 04 |.|^2 and the row sum (rpv2.cu:150-157, 171-197)
                 if (ka >= R1B - 2) u[15] = make_float2(0.f, 0.f); // the two clipped bins
