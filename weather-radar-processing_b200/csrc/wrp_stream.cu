@@ -481,9 +481,10 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
         {
             const uint32_t dep = __float_as_uint(v[R - 1].x) & (uint32_t)p.zero;
             if constexpr (K::STAGE_SEPARATE) {
-                if (has_next) issue_tile(nvp, nt, dep); // the warp's region is in registers: fetch its share of the next tile
-                // (a TMA L2 prefetch of the tile after next, cp.async.bulk.prefetch.tensor, was measured: +0.5 % on
-                // 1024 x 512, -12 % on 4096 x 1024 — the wait for a tile is transfer time under a busy HBM, not DRAM latency)
+                // the warp's region is in registers: fetch its share of the next tile.  (Issuing after the second /
+                // third / last butterfly stage instead was measured 2-3 % slower; a TMA L2 prefetch of the tile
+                // after next +0.5 % on 1024 x 512 and -12 % on 4096 x 1024.)
+                if (has_next) issue_tile(nvp, nt, dep);
             }
         }
         fft_dit_after_stage1<R, -1>(v);
