@@ -1,48 +1,58 @@
 #!/usr/bin/env python
-"""Turn the ncu artefacts in gpurun_out/ into the committed summaries under profiles/."""
-import csv, json, os, subprocess, sys, collections
+"""Turn the artefacts tools/profile.sh left in gpurun_out/ into the committed summaries under profiles/:
+  <tag>_launches.csv / <tag>_launches.md   ncu launch list of the bench command (shares, not absolutes)
+  <tag>_stream_ncu_summary.txt             counters of one chain_stream_kernel launch (ncu --set full)
+  <tag>_stream_hot_sass.txt                stall reasons, instruction mix, hottest SASS lines
+  latest_summary.json                      DRAM bytes per launch, read by bench.py for roofline.traffic
+  <tag>_bench_line.json, <tag>_bench_reference_line.json
+usage: python tools/make_profiles.py [tag]   (no GPU needed; ncu -i reads the report)"""
+import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-os.makedirs(P, exist_ok=True)
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+CMD = ("python bench.py --steps 2 --warmup 3 --cpu-sample 1 --sustain-seconds 0.001 --stress-sectors 8 --volume-steps 0 "
+       "--skip-reference-gpu")
 # 1. launch list
-rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 8]
-hdr = rows[0]; ni, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
-agg = collections.OrderedDict()
+raw = open(os.path.join(G, "launches.csv")).read()
+rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
+h = rows[0]
+ni, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+per = collections.OrderedDict()
 for r in rows[1:]:
-    k = (r[ni].split("(")[0][:70], r[gi], r[bi]); agg.setdefault(k, []).append(float(r[vi].replace(",", "")))
-with open(os.path.join(P, f"{tag}_launches.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 80 python bench.py --steps 5 --warmup 3 --cpu-sample 2 --stress-sectors 0\n")
-    f.write("# per-launch device time (cold cache, serialised: compare shares, not absolutes)\n")
-    tot = sum(sum(v) for v in agg.values())
-    f.write(f"{'kernel':72s} {'grid':>14s} {'block':>12s} {'n':>4s} {'mean_us':>10s} {'share':>7s}\n")
-    for (k, g, b), v in agg.items():
-        f.write(f"{k:72s} {g:>14s} {b:>12s} {len(v):4d} {sum(v)/len(v)/1e3:10.2f} {sum(v)/tot:7.3f}\n")
-    first = [float(r[vi].replace(",", "")) / 1e3 for r in rows[1:9]]
-    f.write(f"# launches 1-8 = 3 warm-up + 5 timed steps (one 143-sector launch of {rows[1][ni].split('(')[0]} each, the whole step): "
-            f"mean {sum(first)/8:.1f} us;\n# launches 9-24 = the two side-figure forms (chain_forms in the bench line), then the e2e leg "
-            f"(decode_wire_kernel + chain kernel per 16-sector piece) and the wire-resident leg.\n")
-# 2. full capture summary + hot SASS
-rep = os.path.join(G, "prof_chain.ncu-rep")
-s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
-open(os.path.join(P, f"{tag}_chain_ncu_summary.txt"), "w").write("# ncu --set full --clock-control none --import-source on -k regex:chain_ -s 4 -c 1 python bench.py --steps 5 --warmup 3 (one 143-sector launch)\n" + s)
-h = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stalls.py"), rep, "40"], capture_output=True, text=True).stdout
-open(os.path.join(P, f"{tag}_chain_hot_sass.txt"), "w").write("# stall reasons, instruction mix and the SASS instructions with most warp-stall samples (ncu --page source)\n" + h)
-# 3. traffic for bench.py
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines())); hd, un, d = rr[0], rr[1], rr[2:]
+    v = float(r[vi].replace(",", ""))
+    per.setdefault(r[ni].split("(")[0], []).append({"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(r[ui], v / 1e3))
+tot = sum(sum(v) for v in per.values())
+open(os.path.join(P, f"{tag}_launches.csv"), "w").write(raw)
+md = [f"# ncu launch list of the bench command ({tag}, 1 x B200)\n",
+      f"Command (exited 0 without ncu immediately before): `{CMD}`",
+      "under `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv`.",
+      "Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.\n",
+      "| kernel | launches | total us | share of all kernel time | mean us |", "|---|---|---|---|---|"]
+for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+    md.append(f"| {k} | {len(v)} | {sum(v):.1f} | {sum(v) / tot:.3f} | {sum(v) / len(v):.1f} |")
+open(os.path.join(P, f"{tag}_launches.md"), "w").write("\n".join(md) + "\n")
+# 2. full capture
+rep = os.path.join(G, "prof_bench_stream.ncu-rep")
+run = lambda tool, *a: subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep, *a], capture_output=True, text=True).stdout
+open(os.path.join(P, f"{tag}_stream_ncu_summary.txt"), "w").write(
+    f"# ncu --set full --clock-control none --import-source on -k regex:chain_stream_kernel -s 4 -c 1 {CMD}\n" + run("ncu_summary.py"))
+open(os.path.join(P, f"{tag}_stream_hot_sass.txt"), "w").write(
+    "# stall reasons, instruction mix and the SASS instructions with most warp-stall samples of the launch above\n" + run("ncu_stalls.py", "40"))
+rr = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+hd, un, d = rr[0], rr[1], rr[2:]
 def col(name):
-    i = hd.index(name); sc = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[un[i]]
-    return [float(x[i]) * sc for x in d]
+    i = hd.index(name)
+    return float(d[0][i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[un[i]]
 rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
-traffic = sum(a + b for a, b in zip(rd, wr)) / len(rd)
-kname = d[0][hd.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0].strip()
-summ = {kname + "_dram_bytes_per_launch": traffic, "dram_read_bytes": sum(rd)/len(rd), "dram_write_bytes": sum(wr)/len(wr),
-        "launches_profiled": len(rd), "source": f"profiles/{tag}_chain_ncu_summary.txt", "sectors_per_launch": 143}
-json.dump(summ, open(os.path.join(P, "latest_summary.json"), "w"), indent=1)
-bl = open(os.path.join(G, "bench_plain.log")).read().strip().splitlines()[-1]
-open(os.path.join(P, f"{tag}_bench_line.json"), "w").write(bl + "\n")
-ref = os.path.join(G, "bench_reference.log")
-if os.path.exists(ref):
-    open(os.path.join(P, f"{tag}_bench_reference_line.json"), "w").write(open(ref).read().strip().splitlines()[-1] + "\n")
-print(json.dumps(summ))
+json.dump({"chain_stream_kernel_dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+           "algorithmic_bytes_per_launch": 143 * 12587008, "traffic_over_algorithmic": (rd + wr) / (143 * 12587008),
+           "source": f"profiles/{tag}_stream_ncu_summary.txt", "sectors_per_launch": 143},
+          open(os.path.join(P, "latest_summary.json"), "w"), indent=1)
+# 3. bench lines
+for src, dst in (("bench.json", "bench_line.json"), ("bench_ref.json", "bench_reference_line.json")):
+    p = os.path.join(G, src)
+    if os.path.exists(p):
+        lines = [l for l in open(p) if l.startswith("{")]
+        if lines:
+            open(os.path.join(P, f"{tag}_{dst}"), "w").write(lines[-1])
+print("profiles written for", tag)
