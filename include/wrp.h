@@ -65,8 +65,10 @@ typedef enum {
      * tile's rows k < M/2 straight into the per-gate sums that stages 03-08 reduce to in energy form
      * (Parseval: row energy minus the DC bin and the two clipped bins); ZdB/ZDR when a sector's hh
      * and vv planes are complete.  There is no range -> Doppler hand-off buffer and no CTA ever
-     * waits for another.  Built for M = 1024 (planar or wire input, decode on the load path) and
-     * M = 4096 (planar; wire goes through a decode pre-pass), any power-of-two N in [64, 8192].
+     * waits for another.  Built for M = 1024 (planar or wire input) and M = 4096 (planar; wire goes
+     * through a decode pre-pass), any power-of-two N in [64, 8192].  Wire records with three channels
+     * run on chain_wire3_kernel (same file): a tile is 4 record columns x (hh, vv, vh), its raw
+     * 48-byte rows arrive by TMA and are decoded in the first FFT pass (sector.cpp:52-62 on the GPU).
      * doppler_form = WRP_DOPPLER_FFT or chain_impl = WRP_CHAIN_QUEUE select the two-kind work queue
      * (chain_persistent_kernel: range tiles + Doppler blocks with an L2-resident hand-off ring,
      * M = 1024 / 4096, N = 512 / 1024), which can run the literal Doppler transform, shift, clip
@@ -224,7 +226,7 @@ int wrp_dump_stage(wrp_handle *h, int sector_in_batch, int stage, int channel, v
 unsigned long long wrp_launch_count(const wrp_handle *h);
 
 /* Name of the kernel that carries the chain for this handle's configuration
- * ("chain_stream_kernel", "chain_persistent_kernel", "range_fft_kernel", "staged cascade") —
+ * ("chain_stream_kernel", "chain_wire3_kernel", "chain_persistent_kernel", "range_fft_kernel", "staged cascade") —
  * what bench.py's roofline object and the ncu launch list refer to. */
 const char *wrp_chain_kernel_name(const wrp_handle *h);
 
