@@ -127,7 +127,10 @@ typedef struct {
     int x2_ring;       /* queue kernel: sector slots of the hand-off ring (0 = default)  */
     int evict_first;   /* queue kernel: stream the input through L2 evict-first (-1 = default, 0 off, 1 on) */
     int debug;         /* development switches: 16 = dependency counters of the queue kernel on stderr;
-                        * 32 = planar input uses the wire path's work partition (bit-identical sums, tests) */
+                        * 32 = planar input uses the one-channel wire kernel's work partition (bit-identical sums, tests);
+                        * 128 = three-channel wire input keeps the one-channel-per-CTA kernel (A/B against chain_wire3_kernel);
+                        * bits 8..17 = TMA L2 promotion of the planar tile loads in bytes (0 / 64 / 128 / 256; measured
+                        * useless, default 0) */
 } wrp_config;
 
 typedef struct wrp_handle wrp_handle;
