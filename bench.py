@@ -234,6 +234,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class _DeviceArray:
+    """A raw device allocation seen by torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def peer_mapped_buffers(torch, dist, dev, world, rank, shape, count):
+    """`count` zero-filled float32 buffers of `shape` on this rank's device, each mapped into every other rank's
+    address space (CUDA IPC; the ranks are processes of one box, the mapping goes over NVLink).  Returns
+    (tensors, ptrs): tensors[i] = this rank's buffer i, ptrs[i][r] = rank r's buffer i as a device pointer valid
+    in THIS process (ptrs[i][rank] is the local one).  These are the mirrors of wrp_set_product_mirrors."""
+    from cuda.bindings import runtime as cudart
+
+    def ck(ret):
+        err, *rest = ret if isinstance(ret, tuple) else (ret,)
+        if int(err) != 0:
+            raise SystemExit(f"bench.py: CUDA runtime error {err} while mapping the peers' volume buffers")
+        return rest[0] if rest else None
+
+    ck(cudart.cudaSetDevice(dev.index))
+    nbytes = 4 * int(np.prod(shape))
+    tensors, ptrs = [], []
+    for _ in range(count):
+        ptr = int(ck(cudart.cudaMalloc(nbytes)))
+        ck(cudart.cudaMemset(ptr, 0, nbytes))
+        handle = ck(cudart.cudaIpcGetMemHandle(ptr))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.reserved))
+        row = []
+        for r in range(world):
+            if r == rank:
+                row.append(ptr)
+                continue
+            h = cudart.cudaIpcMemHandle_t()
+            h.reserved = handles[r]
+            row.append(int(ck(cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess))))
+        tensors.append(torch.as_tensor(_DeviceArray(ptr, shape), device=dev))
+        ptrs.append(row)
+    torch.cuda.synchronize()
+    dist.barrier()
+    return tensors, ptrs
+
+
 def _dist_env():
     return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
             int(os.environ.get("LOCAL_RANK", "0")))
@@ -360,7 +404,13 @@ def run_ours(args):
     E = 9
     vol = [torch.empty((E, S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)]
     d_out = [vol[0][0], vol[1][0]]  # scratch views for the side legs below
-    gathered = [torch.empty((world, E, S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    fused = world > 1 and args.gather == "fused"
+    if fused:
+        # the fused gather: every rank's kernels store their products into all ranks' volume buffers themselves
+        gathered, peer_ptrs = peer_mapped_buffers(torch, dist, dev, world, rank, (world, E, S, M // 2, 2), 2)
+        flag = torch.zeros(1, device=dev)
+    else:
+        gathered = [torch.zeros((world, E, S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
     chain = wrp.RadarChain(local_rank, max_batch=args.host_piece)
     info = chain.info
     stream = torch.cuda.current_stream()
@@ -368,28 +418,40 @@ def run_ours(args):
     gather_done = [None, None]
     step_no = [0]
     n_gathers = [0]
+    slot_bytes = S * (M // 2) * 2 * 4  # one elevation of one rank
 
     def gather(v):
-        """The path's one exchange: the finished product volume, all-gathered on the side stream.  (A DMA gather —
-        every rank cudaMemcpyAsync-ing its slice into the peers' buffers mapped through CUDA IPC, no SM involved —
-        was measured: equal at N = 2, 31 % slower at N = 8; profiles/r02_ab_variants.md.)"""
+        """End of a volume.  --gather nccl: the finished product volume is all-gathered on the side stream.
+        --gather fused (default): the kernels have already stored it into every rank's buffer through the product
+        mirrors; what is left is the completion handshake a consumer needs — one 4-byte all-reduce on the side
+        stream, behind this rank's last kernel of the volume.  (Also measured: a DMA gather, cudaMemcpyAsync into
+        the IPC-mapped peers — equal at N = 2, 31 % slower at N = 8; profiles/r02_ab_variants.md.)"""
         ready = torch.cuda.Event()
         ready.record(stream)
         side.wait_event(ready)
         with torch.cuda.stream(side):
-            dist.all_gather_into_tensor(gathered[v], vol[v])
+            if fused:
+                dist.all_reduce(flag)
+            else:
+                dist.all_gather_into_tensor(gathered[v], vol[v])
             gather_done[v] = torch.cuda.Event()
             gather_done[v].record(side)
         n_gathers[0] += 1
 
     def step():
-        """One PPI elevation per GPU.  After the ninth elevation the rank's product volume is all-gathered on
-        the side stream while the next volume's first elevations already run."""
+        """One PPI elevation per GPU.  After the ninth elevation the product volume is complete on every rank
+        (fused: stored by the kernels; nccl: all-gathered on the side stream) while the next volume's first
+        elevations already run."""
         e, v = step_no[0] % E, (step_no[0] // E) & 1
         step_no[0] += 1
         if world > 1 and e == 0 and gather_done[v] is not None:
-            stream.wait_event(gather_done[v])  # the gather that read this volume buffer two volumes ago
-        chain.process_device(d_in.data_ptr(), S, vol[v][e].data_ptr(), stream.cuda_stream)
+            stream.wait_event(gather_done[v])  # everybody is done with this volume buffer (two volumes ago)
+        if fused:
+            off = (rank * E + e) * slot_bytes  # this rank's slice [rank][e] of a volume buffer
+            chain.set_product_mirrors([peer_ptrs[v][r] + off for r in range(world) if r != rank])
+            chain.process_device(d_in.data_ptr(), S, peer_ptrs[v][rank] + off, stream.cuda_stream)
+        else:
+            chain.process_device(d_in.data_ptr(), S, vol[v][e].data_ptr(), stream.cuda_stream)
         if world > 1 and e == E - 1:
             gather(v)
 
@@ -432,7 +494,16 @@ def run_ours(args):
     ms = _max_over_ranks(ms, dev, world)
     value = world * S * steps / (ms * 1e-3)
     chain_kernel = chain.chain_kernel
-    if world > 1:  # the last gathered volume holds every rank's products
+    if fused:
+        chain.set_product_mirrors(())
+        # the volume buffers the kernels filled over NVLink against an NCCL all-gather of each rank's own slice
+        for v in range(2):
+            check = torch.empty_like(gathered[v])
+            dist.all_gather_into_tensor(check, gathered[v][rank].contiguous())
+            if not torch.equal(check, gathered[v]) or not torch.isfinite(gathered[v][:, 0, :, 1:]).all():
+                raise SystemExit("bench.py: the fused gather left a wrong product volume")
+        del check
+    elif world > 1:  # the last gathered volume holds every rank's products
         v = ((step_no[0] - 1) // E) & 1
         if not torch.equal(gathered[v][rank], vol[v]) or not torch.isfinite(gathered[v][:, 0, :, 1:]).all():
             raise SystemExit("bench.py: all-gathered product volume is wrong")
@@ -541,9 +612,14 @@ def run_ours(args):
             "config": dict(CONFIG),
             "run": {"sectors_per_step_per_gpu": S, "input_fmt": "c64_planar", "chunk_sectors": int(info.chunk_sectors),
                     "l2": f"input batch {d_in.numel() * 4 / 1e6:.0f} MB per GPU > L2 {info.l2_bytes / 1e6:.0f} MB, no flush needed",
-                    "parallelism": f"sectors sharded over {world} GPU(s); the product volume (9 elevations x 143 sectors per "
-                                   "GPU) is all-gathered once per volume on a side stream, overlapped with the next "
-                                   "volume's kernels; the timed region ends after the last gather",
+                    "parallelism": f"sectors sharded over {world} GPU(s); " + (
+                        "fused gather: the chain kernel's epilogue stores every product into all ranks' volume buffers "
+                        "(peer-mapped, NVLink) itself; per volume (9 elevations x 143 sectors per GPU) one 4-byte all-reduce "
+                        "on a side stream as the completion handshake; the timed region ends after the last handshake; the "
+                        "volume buffers are checked against an NCCL all-gather afterwards" if fused else
+                        "the product volume (9 elevations x 143 sectors per GPU) is all-gathered once per volume on a side "
+                        "stream, overlapped with the next volume's kernels; the timed region ends after the last gather"),
+                    "gather": "fused" if fused else ("nccl" if world > 1 else None),
                     "gathers_in_timed_region": n_gathers_timed},
             "iq_gbs": value * ALGO_BYTES_C64 / 1e9,
             "chain_hbm_frac": value / world * ALGO_BYTES_C64 / 1e9 / peak,
@@ -621,6 +697,8 @@ def main():
                     help="sectors of the 4096x1024 stress shape kept resident per GPU (BASELINE config 5; 0 = skip)")
     ap.add_argument("--volume-steps", type=int, default=3,
                     help="volume scans timed for BASELINE config 4 (9 x 143 wire sectors from pinned host memory; 0 = skip)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: product volume stored into every rank's buffer by the kernels (fused) or all-gathered by NCCL")
     ap.add_argument("--workload", default="sector", choices=["sector", "volume"],
                     help="sector: the default line (every leg); volume: only config 4 as its own line")
     ap.add_argument("--cpu-sample", type=int, default=0, help="non-zero: shorten the CPU baseline leg (profiling runs)")

@@ -241,6 +241,21 @@ const char *wrp_chain_kernel_name(const wrp_handle *h);
  * does not run the streaming kernel. */
 int wrp_set_stage02_tap(wrp_handle *h, void *dev_x2);
 
+/* The fused gather (the reference collects every sector's products into one result[]
+ * volume, rpv2.cu:607, 736).  While n_mirrors > 0, wrp_process_device and wrp_process_host_to_device
+ * store every (ZdB, ZDR) pair not only at dev_out[i] but also at mirrors[m][i] for every m — the
+ * same float index relative to the mirror as relative to dev_out of that call.  A mirror is any
+ * device-accessible address: normally the slice "this device's units" of the product volume that
+ * lives on ANOTHER device of the box (peer access enabled, or a CUDA-IPC mapping of another
+ * process's buffer), so that the streaming kernel's epilogue writes the volume over NVLink itself
+ * and no collective or copy follows it.  The stores are complete when the stream work of the call
+ * has completed (the usual CUDA rule for peer writes); a consumer on the other device still needs
+ * that one event / barrier.  Kernels other than the streaming ones copy dev_out to the mirrors on
+ * the same stream instead.  The pointer array is copied; n_mirrors = 0 switches it off.
+ * wrp_process_host, wrp_submit/wrp_collect and the staged dumps ignore mirrors. */
+#define WRP_MAX_PRODUCT_MIRRORS 8
+int wrp_set_product_mirrors(wrp_handle *h, float *const *mirrors, int n_mirrors);
+
 /* Per-kernel CUDA-event timing. enable: 1 start accumulating / 0 stop. */
 int wrp_profile_enable(wrp_handle *h, int enable);
 int wrp_profile_read(wrp_handle *h, wrp_profile *out, int reset);

@@ -768,3 +768,63 @@ def test_run_to_run_determinism_stress(wrp, sectors, fmt, S, reps):
             torch.cuda.synchronize()
             bad += int(not torch.equal(out.view(torch.int32), ref.view(torch.int32)))
     assert bad == 0, f"{bad} of {reps} launches differ from the first"
+
+
+@pytest.mark.parametrize("case", ["planar", "wire3", "wire2", "m4096", "queue"])
+def test_product_mirrors_fused_gather(wrp, sectors, case):
+    """wrp_set_product_mirrors: the kernels store every product also at the same index of each mirror (the fused
+    gather — on a multi-GPU box the mirrors are the peers' volume buffers).  Here the mirrors are two more buffers
+    on the same device, at an offset, and must equal the primary output bit for bit for every kernel family —
+    also through the host-to-device path, whose pieces of max_batch sectors are separate launches."""
+    torch = pytest.importorskip("torch")
+    m, n, c, kw = M, N, 3, {}
+    if case in ("wire3", "wire2"):
+        c = 3 if case == "wire3" else 2
+        kw = dict(input_fmt=wrp.FMT_WIRE_I16BE, n_channels=c)
+    elif case == "m4096":
+        m, n, c = 4096, 512, 2
+        kw = dict(n_rows_M=m, n_cols_N=n, n_channels=c)
+    elif case == "queue":
+        kw = dict(chain_impl=wrp.CHAIN_QUEUE)
+    S = 5
+    if case == "m4096":
+        batch = np.stack([wrp.synth.to_planar(wrp.synth.make_sector_int16(m, n, s % 2, 0), c) for s in range(S)])
+    elif case.startswith("wire"):
+        batch = np.stack([wrp.synth.to_wire(sectors[s % 3]) for s in range(S)])
+    else:
+        batch = np.stack([wrp.synth.to_planar(sectors[s % 3]) for s in range(S)])
+    raw = batch.view(np.uint8).reshape(-1)
+    d_in = torch.from_numpy(raw).cuda()
+    d_out = torch.zeros((S, m // 2, 2), device="cuda")
+    pad = 3 * (m // 2) * 2  # the mirrors start three sectors into larger buffers
+    mir = [torch.full((S + 4, m // 2, 2), -7.0, device="cuda") for _ in range(2)]
+    ptrs = [t.data_ptr() + pad * 4 for t in mir]
+    with wrp.RadarChain(0, max_batch=2, **kw) as ch:
+        ch.set_product_mirrors(ptrs)
+        ch.process_device(d_in.data_ptr(), S, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()
+        assert np.isfinite(out[:, 1:, 0]).all()
+        for t in mir:
+            got = t.cpu().numpy()
+            assert np.array_equal(got[3:3 + S], out), case
+            assert (got[:3] == -7.0).all() and (got[3 + S:] == -7.0).all()  # nothing outside the slice
+            t.fill_(-7.0)
+        # host -> device in pieces of max_batch sectors: every piece lands at its own offset of the mirrors
+        d_out.zero_()
+        ch.process_host_to_device(batch, S, d_out.data_ptr())
+        out2 = d_out.cpu().numpy()
+        for t in mir:
+            assert np.array_equal(t.cpu().numpy()[3:3 + S], out2), case
+            t.fill_(-7.0)
+        # switched off again: the mirrors stay untouched; host-destination calls never mirror
+        ch.set_product_mirrors(())
+        ch.process_device(d_in.data_ptr(), S, d_out.data_ptr(), 0)
+        torch.cuda.synchronize()
+        ch.set_product_mirrors(ptrs)
+        ch.process_host(batch, S)
+        assert all((t == -7.0).all().item() for t in mir)
+        with pytest.raises(Exception):
+            ch.set_product_mirrors([ptrs[0] + 4])  # not 8-byte aligned
+        with pytest.raises(Exception):
+            ch.set_product_mirrors([ptrs[0]] * 9)  # more than WRP_MAX_PRODUCT_MIRRORS

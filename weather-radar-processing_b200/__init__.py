@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = (
     "wrp_get_info", "wrp_get_constants", "wrp_process_device", "wrp_process_host",
     "wrp_submit", "wrp_collect", "wrp_alloc_pinned", "wrp_free_pinned", "wrp_dump_stage",
     "wrp_launch_count", "wrp_profile_enable", "wrp_profile_read", "wrp_pack_products",
-    "wrp_chain_kernel_name", "wrp_set_stage02_tap", "wrp_process_host_to_device",
+    "wrp_chain_kernel_name", "wrp_set_stage02_tap", "wrp_set_product_mirrors", "wrp_process_host_to_device",
     "wrp_volume_create", "wrp_volume_shard", "wrp_volume_process", "wrp_volume_last_error", "wrp_volume_destroy",
 )
 
@@ -131,6 +131,7 @@ def lib():
         L.wrp_chain_kernel_name.argtypes = [vp]
         L.wrp_chain_kernel_name.restype = C.c_char_p
         L.wrp_set_stage02_tap.argtypes = [vp, vp]
+        L.wrp_set_product_mirrors.argtypes = [vp, C.POINTER(vp), ip]
         L.wrp_process_host_to_device.argtypes = [vp, vp, ip, vp]
         L.wrp_volume_create.argtypes = [C.POINTER(Config), C.POINTER(ip), ip, ip, ip, C.POINTER(vp)]
         L.wrp_volume_shard.argtypes = [vp, ip, C.POINTER(ip), C.POINTER(ip)]
@@ -262,6 +263,14 @@ class RadarChain:
         """Streaming kernel only: also store the range-FFT rows k < M/2 it folds to device memory
         [sector][channel][M/2][N] complex64 at dev_ptr (None switches the tap off)."""
         self._check(lib().wrp_set_stage02_tap(self._h, dev_ptr))
+
+    def set_product_mirrors(self, dev_ptrs=()):
+        """The fused gather (wrp_set_product_mirrors): process_device / process_host_to_device also store
+        every product at the same float index of each mirror — device pointers, normally peer-mapped
+        slices of the product volume on the other devices of the box.  () switches it off."""
+        ptrs = [int(p) for p in dev_ptrs]
+        arr = (C.c_void_p * max(len(ptrs), 1))(*ptrs)
+        self._check(lib().wrp_set_product_mirrors(self._h, arr, len(ptrs)))
 
     def constants(self):
         """(hamming[M,N], taps[ma_taps], fft_ma[N] complex) — rpv2.cu:222-281."""

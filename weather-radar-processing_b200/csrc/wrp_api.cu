@@ -401,6 +401,20 @@ int wrp_set_stage02_tap(wrp_handle *h, void *dev_x2)
     return WRP_OK;
 }
 
+int wrp_set_product_mirrors(wrp_handle *h, float *const *mirrors, int n_mirrors)
+{
+    if (!h) return WRP_ERR_INVALID;
+    if (n_mirrors < 0 || n_mirrors > WRP_MAX_PRODUCT_MIRRORS || (n_mirrors > 0 && !mirrors))
+        return fail(h, WRP_ERR_INVALID, "wrp_set_product_mirrors: n_mirrors must be in [0, WRP_MAX_PRODUCT_MIRRORS]");
+    for (int m = 0; m < n_mirrors; m++) {
+        if (!mirrors[m] || ((uintptr_t)mirrors[m] & 7)) // the kernels store (ZdB, ZDR) pairs
+            return fail(h, WRP_ERR_INVALID, "wrp_set_product_mirrors: a mirror is NULL or not 8-byte aligned");
+        h->mirrors[m] = mirrors[m];
+    }
+    h->n_mirrors = n_mirrors;
+    return WRP_OK;
+}
+
 // ---- profiling ------------------------------------------------------------------------
 static cudaEvent_t get_event(wrp_handle *h)
 {
@@ -468,8 +482,11 @@ int wrp_profile_read(wrp_handle *h, wrp_profile *out, int reset)
 }
 
 // ---- HBM-resident batch -----------------------------------------------------------------
+// mirror_off: float offset of dev_out inside the caller's product buffer (the mirrors take the same offset);
+// mirror_off == NO_MIRRORS: this call's products are not mirrored (host destination, ring submissions)
+static constexpr size_t NO_MIRRORS = ~(size_t)0;
 static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors, float *dev_out,
-                               cudaStream_t st)
+                               cudaStream_t st, size_t mirror_off = NO_MIRRORS)
 {
     const wrp_config &c = h->cfg;
     const int M = c.n_rows_M, N = c.n_cols_N, C = c.n_channels;
@@ -479,6 +496,8 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
         const int S = n_sectors - s0 < h->chunk ? n_sectors - s0 : h->chunk;
         const uint8_t *in = (const uint8_t *)dev_iq + (size_t)s0 * in_bytes;
         float *out = dev_out + (size_t)s0 * out_floats;
+        const int n_mirrors = mirror_off == NO_MIRRORS ? 0 : h->n_mirrors;
+        bool mirrored_by_kernel = false;
         if (c.mode == WRP_MODE_STAGED) {
             unsigned long long n = 0;
             {
@@ -505,6 +524,9 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 p.tile_tw = h->fused.tile_tw;
                 p.in = chain_in;
                 p.out = out;
+                for (int m = 0; m < n_mirrors; m++) p.mirror[m] = h->mirrors[m] + mirror_off + (size_t)s0 * out_floats;
+                p.n_mirrors = n_mirrors;
+                mirrored_by_kernel = true;
                 p.power = h->power;
                 p.x2_tap = h->x2_tap ? h->x2_tap + (size_t)s0 * C * (M / 2) * N : nullptr;
                 p.scratch = h->stream_scratch;
@@ -557,6 +579,10 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 }
             }
         }
+        if (!mirrored_by_kernel) // the other kernels: a copy per mirror behind them on the same stream
+            for (int m = 0; m < n_mirrors; m++)
+                CK(h, cudaMemcpyAsync(h->mirrors[m] + mirror_off + (size_t)s0 * out_floats, out,
+                                      (size_t)S * out_floats * sizeof(float), cudaMemcpyDefault, st));
         h->prof.sectors += h->profiling ? S : 0;
     }
     return WRP_OK;
@@ -570,7 +596,7 @@ int wrp_process_device(wrp_handle *h, const void *dev_iq, int n_sectors, float *
     if (n_sectors == 0) return WRP_OK;
     if (!dev_iq || !dev_out) return fail(h, WRP_ERR_INVALID, "wrp_process_device: NULL buffer");
     CK(h, cudaSetDevice(h->device));
-    return process_device_impl(h, dev_iq, n_sectors, dev_out, (cudaStream_t)cuda_stream);
+    return process_device_impl(h, dev_iq, n_sectors, dev_out, (cudaStream_t)cuda_stream, 0);
 }
 
 // ---- pinned ring / host path ----------------------------------------------------------------
@@ -601,7 +627,8 @@ static bool host_ptr_is_pinned(const void *p)
 
 // enqueue one ring slot: H2D on the slot's copy stream, kernels on the compute stream,
 // D2H back on the slot stream; slot.done fires when the products are in pinned_out.
-static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, int n, float *dev_dst = nullptr)
+static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, int n, float *dev_dst = nullptr,
+                        size_t mirror_off = NO_MIRRORS)
 {
     const wrp_config &c = h->cfg;
     const size_t in_bytes = input_bytes_per_sector(c) * (size_t)n;
@@ -615,7 +642,8 @@ static int enqueue_slot(wrp_handle *h, wrp::RingSlot &s, const void *host_iq, in
     CK(h, cudaMemcpyAsync(s.dev_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
     CK(h, cudaEventRecord(s.h2d_done, s.stream));
     CK(h, cudaStreamWaitEvent(h->compute_stream, s.h2d_done, 0));
-    const int rc = process_device_impl(h, s.dev_in, n, dev_dst ? dev_dst : s.dev_out, h->compute_stream);
+    const int rc = process_device_impl(h, s.dev_in, n, dev_dst ? dev_dst : s.dev_out, h->compute_stream,
+                                       dev_dst ? mirror_off : NO_MIRRORS);
     if (rc != WRP_OK) return rc;
     CK(h, cudaEventRecord(s.done, h->compute_stream));
     if (!dev_dst) { // products back to the host through the slot's pinned buffer
@@ -710,7 +738,7 @@ static int process_host_impl(wrp_handle *h, const void *host_iq, int n_sectors, 
         rc = ensure_slot(h, s);
         if (rc != WRP_OK) return rc;
         rc = enqueue_slot(h, s, (const uint8_t *)host_iq + (size_t)s0 * in_bytes, n,
-                          dev_out ? dev_out + (size_t)s0 * out_floats : nullptr);
+                          dev_out ? dev_out + (size_t)s0 * out_floats : nullptr, (size_t)s0 * out_floats);
         if (rc != WRP_OK) return rc;
         inflight[slot] = Piece{s0, n};
     }

@@ -90,6 +90,8 @@ struct wrp_handle {
     int *stream_cnt = nullptr;
     float2 wcol[2][8] = {};
     float2 *x2_tap = nullptr; // wrp_set_stage02_tap (caller-owned)
+    float *mirrors[WRP_MAX_PRODUCT_MIRRORS] = {}; // wrp_set_product_mirrors (caller-owned, usually peer-mapped)
+    int n_mirrors = 0;
     // queue / v1 kernels: range -> Doppler hand-off, [ring or chunk][C][M/2][N] float2, L2-resident
     float2 *x2 = nullptr;
     float2 *decoded = nullptr; // [chunk][C][M][N] planar scratch for wire input (decode pre-pass)

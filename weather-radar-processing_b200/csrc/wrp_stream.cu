@@ -90,6 +90,15 @@ template <int Q, bool WIRE> struct Cfg {
     static_assert((Q == 1 ? 2 : 1) * (SMEM + 1024 + 64) <= 233472, "shared memory per SM");
 };
 
+// Stage 09/10 store (rpv2.cu:199-213 writes result[] of the sector; rpv2.cu:607, 736 collect the volume).  With
+// product mirrors set the kernel is its own gather: the (ZdB, ZDR) pair also goes to the same index of every
+// mirror — peer-mapped buffers of the other devices over NVLink — 4 KiB per sector and peer against 12.6 MB read,
+// fire-and-forget stores from the epilogue, no collective kernel and no copy afterwards.
+__device__ __forceinline__ void store_product(const StreamParams &p, size_t idx, float2 v)
+{
+    reinterpret_cast<float2 *>(p.out)[idx] = v;
+    for (int m = 0; m < p.n_mirrors; ++m) reinterpret_cast<float2 *>(p.mirror[m])[idx] = v;
+}
 
 // One staged row of T columns x[0..T) (already scaled by wd(j)) folded into a gate's seven sums.
 //   E += sum |x_c|^2,  Y_0 += sum x_c,  Y_m += tw_m * S_m  with  S_m = sum_c (-1)^c e^{-i theta_m c} x_c.
@@ -613,8 +622,7 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     p.power[(size_t)plane * hm + k] = pw;
                     if (p.C == 1) { // stage 09 only (rpv2.cu:199-213 with a single channel)
                         const float rg = (float)k * p.range_res;
-                        reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
-                            make_float2(10.f * log10f(rg * rg * p.calib * pw), 0.f);
+                        store_product(p, (size_t)sector * hm + k, make_float2(10.f * log10f(rg * rg * p.calib * pw), 0.f));
                     }
                 }
                 if (p.C >= 2 && ch < 2) {
@@ -629,8 +637,8 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                         for (int k = tid; k < hm; k += THREADS) {
                             const float hh = __ldcg(ph + k), vv = __ldcg(pv + k);
                             const float rg = (float)k * p.range_res;
-                            reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
-                                make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv)));
+                            store_product(p, (size_t)sector * hm + k,
+                                          make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv))));
                         }
                     }
                 }
@@ -901,8 +909,8 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
                 for (int k = tid; k < hm; k += THREADS) {
                     const float hh = ph[k], vv = pv[k];
                     const float rg = (float)k * p.range_res;
-                    reinterpret_cast<float2 *>(p.out)[(size_t)sector * hm + k] =
-                        make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv)));
+                    store_product(p, (size_t)sector * hm + k,
+                                  make_float2(10.f * log10f(rg * rg * p.calib * hh), 10.f * (log10f(hh) - log10f(vv))));
                 }
             }
         }

@@ -23,6 +23,8 @@ struct StreamParams {
     // data
     const void *in;         // planar [S][C][M][N] float2, or wire records [S][M][N] x 12 B
     float *out;             // [S][M/2][2]  (ZdB, ZDR)
+    float *mirror[8];       // the fused gather (wrp_set_product_mirrors): every product is also stored at mirror[i][same index];
+    int n_mirrors;          // peer-mapped memory of the other devices of the box (NVLink) or plain device memory
     float *power;           // [S][C][M/2]  row powers (also the hh/vv exchange between the CTAs that finish the planes)
     float2 *x2_tap;         // optional debug tap: range-FFT rows k < M/2, [S][C][M/2][N]; NULL in production
     float *scratch;         // [grid][2][7][M/2] partial sums of planes shared between CTAs

@@ -3,11 +3,13 @@
 // sitdim(0, 0, sector, elevation), rpv2.cu:607, 736) cut into one contiguous unit block per device.
 //
 // One host thread per shard, each with its own libwrp handle (pinned ring, copy streams, compute
-// stream) on its device: H2D of the shard's sectors overlaps compute, the products stay in that
-// device's memory (wrp_process_host_to_device).  The only exchange is the gather of the finished
-// products: every shard copies its slice into the volume buffer on devices[0] with
-// cudaMemcpyPeerAsync — NVLink between peers — and one D2H copy returns the volume.  No collective
-// library is involved and nothing here waits on another device's kernel.
+// stream) on its device: H2D of the shard's sectors overlaps compute.  The only exchange is the
+// gather of the finished products, and it is fused into the chain kernel: the volume buffer lives on
+// devices[0], every other device has peer access to it, and each shard's handle carries its slice
+// of that buffer as a product mirror (wrp_set_product_mirrors) — the kernel's epilogue stores the
+// products over NVLink itself.  Shard 0 writes its slice directly.  One D2H copy returns the volume.
+// A device without peer access to devices[0] falls back to cudaMemcpyPeerAsync of its slice.
+// No collective library is involved and nothing here waits on another device's kernel.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -23,7 +25,8 @@ struct wrp_volume {
     std::vector<int> devices;
     std::vector<wrp_handle *> handles;
     std::vector<float *> dev_out;    // per shard: [n_units of the shard][M/2][2] on its device
-    std::vector<cudaStream_t> stream; // per shard: the gather copy
+    std::vector<cudaStream_t> stream; // per shard: the gather copy (devices without peer access only)
+    std::vector<char> peer;          // per shard: can store into dev_volume directly
     float *dev_volume = nullptr;     // on devices[0]: [U][M/2][2]
     std::string err;
 };
@@ -79,6 +82,7 @@ int wrp_volume_create(const wrp_config *cfg, const int *devices, int n_devices, 
     v->handles.assign(n_devices, nullptr);
     v->dev_out.assign(n_devices, nullptr);
     v->stream.assign(n_devices, nullptr);
+    v->peer.assign(n_devices, 0);
     const int U = n_sectors * n_elevations;
     const size_t slot = (size_t)cfg->n_rows_M * sizeof(float); // 2 * M/2 floats per unit
     auto bail = [&](int rc, const std::string &msg) {
@@ -95,11 +99,13 @@ int wrp_volume_create(const wrp_config *cfg, const int *devices, int n_devices, 
             cudaMalloc((void **)&v->dev_out[g], slot * (size_t)(hi - lo > 0 ? hi - lo : 1)) != cudaSuccess ||
             cudaStreamCreateWithFlags(&v->stream[g], cudaStreamNonBlocking) != cudaSuccess)
             return bail(WRP_ERR_CUDA, std::string("wrp_volume_create: ") + cudaGetErrorString(cudaGetLastError()));
-        if (devices[g] != devices[0]) { // NVLink path for the gather where the devices are peers (best effort)
+        v->peer[g] = devices[g] == devices[0];
+        if (!v->peer[g]) { // NVLink path for the fused gather where the devices are peers
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) == cudaSuccess && can) {
                 const cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
-                if (e != cudaSuccess) cudaGetLastError(); // already enabled is fine
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) v->peer[g] = 1;
+                cudaGetLastError(); // "already enabled" is fine
             }
         }
     }
@@ -139,15 +145,27 @@ int wrp_volume_process(wrp_volume *v, const void *host_iq, float *host_volume)
             rc[g] = WRP_ERR_CUDA, msg[g] = "cudaSetDevice failed";
             return;
         }
-        rc[g] = wrp_process_host_to_device(v->handles[g], (const uint8_t *)host_iq + (size_t)lo * in_bytes, hi - lo,
-                                           v->dev_out[g]);
+        float *slice = (float *)((uint8_t *)v->dev_volume + (size_t)lo * slot);
+        const uint8_t *src = (const uint8_t *)host_iq + (size_t)lo * in_bytes;
+        if (g == 0 || v->devices[g] == v->devices[0]) { // the volume's own device: straight into the slice
+            rc[g] = wrp_process_host_to_device(v->handles[g], src, hi - lo, slice);
+            if (rc[g] != WRP_OK) msg[g] = wrp_last_error(v->handles[g]);
+            return;
+        }
+        if (v->peer[g]) { // fused gather: the kernel's epilogue stores the slice over NVLink
+            rc[g] = wrp_set_product_mirrors(v->handles[g], &slice, 1);
+            if (rc[g] == WRP_OK) rc[g] = wrp_process_host_to_device(v->handles[g], src, hi - lo, v->dev_out[g]);
+            if (rc[g] != WRP_OK) msg[g] = wrp_last_error(v->handles[g]);
+            return;
+        }
+        rc[g] = wrp_process_host_to_device(v->handles[g], src, hi - lo, v->dev_out[g]);
         if (rc[g] != WRP_OK) {
             msg[g] = wrp_last_error(v->handles[g]);
             return;
         }
-        // the gather: this shard's slice of the product volume -> devices[0]
-        cudaError_t e = cudaMemcpyPeerAsync((uint8_t *)v->dev_volume + (size_t)lo * slot, v->devices[0], v->dev_out[g],
-                                            v->devices[g], (size_t)(hi - lo) * slot, v->stream[g]);
+        // no peer access: this shard's slice of the product volume -> devices[0] by DMA
+        cudaError_t e = cudaMemcpyPeerAsync(slice, v->devices[0], v->dev_out[g], v->devices[g], (size_t)(hi - lo) * slot,
+                                            v->stream[g]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream[g]);
         if (e != cudaSuccess) rc[g] = WRP_ERR_CUDA, msg[g] = std::string("gather: ") + cudaGetErrorString(e);
     };
