@@ -27,6 +27,6 @@ with wrp.VolumeScan(list(range(a.gpus)), S, E, input_fmt=wrp.FMT_WIRE_I16BE, max
         vol = vs.process(pin, vol)
     dt = (time.perf_counter() - t0) / a.steps
 ok = bool(np.isfinite(vol[:, 1:]).all() and all(np.allclose(vol[k, 1:], vol[k % 4, 1:], rtol=0, atol=1e-3) for k in range(0, U, 61)))
-print(json.dumps({"workload": f"volume scan {E} x {S} wire sectors, wrp_volume_process (C ABI, threads, peer-copy gather)",
+print(json.dumps({"workload": f"volume scan {E} x {S} wire sectors, wrp_volume_process (C ABI, threads, products stored into the volume on devices[0] by the kernels)",
                   "n_gpus": a.gpus, "ms_per_volume": dt * 1e3, "sectors_per_s": U / dt,
                   "h2d_gbs_per_gpu": U / dt * M * N * 12 / 1e9 / a.gpus, "volume_ok": ok}))
