@@ -31,9 +31,12 @@ reference:
   on all host cores; rank 0 only.
 
 Multi-GPU (torchrun, one rank per GPU): sectors are independent, each rank
-processes its own shard — weak scaling — and the product volume (9 elevations) is all-gathered
-over NCCL once per volume on a side stream, overlapped with the next volume's kernels (the timed
-region ends after the last gather); there is no other collective.
+processes its own shard — weak scaling — and the product volume (9 elevations) is gathered by the
+chain kernel itself: its epilogue stores every product into all ranks' volume buffers (CUDA-IPC
+mapped peers over NVLink, wrp_set_product_mirrors); per volume one 4-byte all-reduce on a side
+stream is the completion handshake, and the timed region ends after the last one.  `--gather nccl`
+(or a box where the peers cannot be mapped) all-gathers the volume with NCCL once per volume on the
+side stream instead.  There is no other collective.
 """
 from __future__ import annotations
 
@@ -245,36 +248,60 @@ def peer_mapped_buffers(torch, dist, dev, world, rank, shape, count):
     """`count` zero-filled float32 buffers of `shape` on this rank's device, each mapped into every other rank's
     address space (CUDA IPC; the ranks are processes of one box, the mapping goes over NVLink).  Returns
     (tensors, ptrs): tensors[i] = this rank's buffer i, ptrs[i][r] = rank r's buffer i as a device pointer valid
-    in THIS process (ptrs[i][rank] is the local one).  These are the mirrors of wrp_set_product_mirrors."""
-    from cuda.bindings import runtime as cudart
+    in THIS process (ptrs[i][rank] is the local one) — the mirrors of wrp_set_product_mirrors.  Returns None on
+    every rank if any rank could not allocate or map (the ranks agree through an all-reduce after each phase, so
+    nobody is left waiting in a collective)."""
 
     def ck(ret):
         err, *rest = ret if isinstance(ret, tuple) else (ret,)
         if int(err) != 0:
-            raise SystemExit(f"bench.py: CUDA runtime error {err} while mapping the peers' volume buffers")
+            raise RuntimeError(f"CUDA runtime error {err}")
         return rest[0] if rest else None
 
-    ck(cudart.cudaSetDevice(dev.index))
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     nbytes = 4 * int(np.prod(shape))
+    local, mine = [], []
+    try:
+        from cuda.bindings import runtime as cudart
+
+        ck(cudart.cudaSetDevice(dev.index))
+        for _ in range(count):
+            ptr = int(ck(cudart.cudaMalloc(nbytes)))
+            ck(cudart.cudaMemset(ptr, 0, nbytes))
+            local.append(ptr)
+            mine.append(bytes(ck(cudart.cudaIpcGetMemHandle(ptr)).reserved))
+        ok = True
+    except Exception as ex:  # noqa: BLE001 - reported, then the NCCL gather takes over
+        print(f"bench.py: rank {rank}: cannot export the volume buffers ({ex})", file=sys.stderr)
+        ok = False
+    if not all_ok(ok):
+        return None
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
     tensors, ptrs = [], []
-    for _ in range(count):
-        ptr = int(ck(cudart.cudaMalloc(nbytes)))
-        ck(cudart.cudaMemset(ptr, 0, nbytes))
-        handle = ck(cudart.cudaIpcGetMemHandle(ptr))
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.reserved))
-        row = []
-        for r in range(world):
-            if r == rank:
-                row.append(ptr)
-                continue
-            h = cudart.cudaIpcMemHandle_t()
-            h.reserved = handles[r]
-            row.append(int(ck(cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess))))
-        tensors.append(torch.as_tensor(_DeviceArray(ptr, shape), device=dev))
-        ptrs.append(row)
-    torch.cuda.synchronize()
-    dist.barrier()
+    try:
+        for i in range(count):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(local[i])
+                    continue
+                h = cudart.cudaIpcMemHandle_t()
+                h.reserved = handles[r][i]
+                row.append(int(ck(cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess))))
+            tensors.append(torch.as_tensor(_DeviceArray(local[i], shape), device=dev))
+            ptrs.append(row)
+        torch.cuda.synchronize()
+        ok = True
+    except Exception as ex:  # noqa: BLE001
+        print(f"bench.py: rank {rank}: cannot map the peers' volume buffers ({ex})", file=sys.stderr)
+        ok = False
+    if not all_ok(ok):
+        return None
     return tensors, ptrs
 
 
@@ -407,9 +434,13 @@ def run_ours(args):
     fused = world > 1 and args.gather == "fused"
     if fused:
         # the fused gather: every rank's kernels store their products into all ranks' volume buffers themselves
-        gathered, peer_ptrs = peer_mapped_buffers(torch, dist, dev, world, rank, (world, E, S, M // 2, 2), 2)
-        flag = torch.zeros(1, device=dev)
-    else:
+        mapped = peer_mapped_buffers(torch, dist, dev, world, rank, (world, E, S, M // 2, 2), 2)
+        if mapped is None:
+            fused = False  # said on stderr; the line's run.gather then reads "nccl"
+        else:
+            gathered, peer_ptrs = mapped
+            flag = torch.zeros(1, device=dev)
+    if not fused:
         gathered = [torch.zeros((world, E, S, M // 2, 2), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
     chain = wrp.RadarChain(local_rank, max_batch=args.host_piece)
     info = chain.info
