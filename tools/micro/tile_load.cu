@@ -79,6 +79,8 @@ struct Params {
     int n_tiles;    // total tiles
     int tiles_per_plane;
     int mode, nbuf;
+    int assign;     // 0: CTA x takes tiles x, x + G, ...; 1: a contiguous run per CTA; g >= 2: groups of g CTAs share a
+                    // contiguous run and interleave its tiles (the g CTAs read g adjacent row segments at the same time)
     unsigned long long *sink;
 };
 
@@ -123,13 +125,28 @@ __global__ void __launch_bounds__(256) load_kernel(const Params p, const __grid_
 
     unsigned long long acc = 0;
     int n_mine = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) ++n_mine;
-    for (int k = 0; k < p.nbuf - 1 && k < n_mine; ++k) issue(blockIdx.x + k * gridDim.x, k);
+    const int G = gridDim.x, x = blockIdx.x;
+    auto tile_of = [&](int k) -> int {
+        if (p.assign == 0) return x + k * G;
+        if (p.assign == 1) return (int)((long long)p.n_tiles * x / G) + k;
+        const int g = p.assign, grp = x / g, j = x - grp * g;
+        return (int)((long long)p.n_tiles * (grp * g) / G) + k * g + j;
+    };
+    if (p.assign == 0) {
+        for (int t = x; t < p.n_tiles; t += G) ++n_mine;
+    } else if (p.assign == 1) {
+        n_mine = (int)((long long)p.n_tiles * (x + 1) / G) - (int)((long long)p.n_tiles * x / G);
+    } else {
+        const int g = p.assign, grp = x / g, j = x - grp * g;
+        const int lo = (int)((long long)p.n_tiles * (grp * g) / G), hi = (int)((long long)p.n_tiles * min((grp + 1) * g, G) / G);
+        n_mine = (hi - lo - j + g - 1) / g;
+    }
+    for (int k = 0; k < p.nbuf - 1 && k < n_mine; ++k) issue(tile_of(k), k);
     for (int k = 0; k < n_mine; ++k) {
         const int buf = k % p.nbuf;
         if (k + p.nbuf - 1 < n_mine) {
             __syncthreads(); // the buffer being refilled was consumed by everybody one iteration ago
-            issue(blockIdx.x + (k + p.nbuf - 1) * gridDim.x, (k + p.nbuf - 1) % p.nbuf);
+            issue(tile_of(k + p.nbuf - 1), (k + p.nbuf - 1) % p.nbuf);
         }
         mbar_wait(&bar[buf], (k / p.nbuf) & 1);
         const uint8_t *src = smem + (size_t)buf * tile_bytes;
@@ -166,6 +183,7 @@ int main(int argc, char **argv)
     struct Cfg {
         const char *name;
         int mode, rows, cols, n_cols, nbuf, ctas_per_sm, threads;
+        int assign = 0;
     };
     const std::vector<Cfg> cfgs = {
         {"cp.async16   8 col x 1024 rows (64 B rows), 1 buf, 2 CTA/SM", 0, 1024, 8, 512, 1, 2, 256},
@@ -179,6 +197,11 @@ int main(int argc, char **argv)
         {"TMA tiled   16 col x 1024 rows (128 B rows), 1 buf, 1 CTA/SM", 1, 1024, 16, 512, 1, 1, 256},
         {"TMA tiled   32 col x 512 rows (256 B rows), 1 buf, 1 CTA/SM", 1, 512, 32, 512, 1, 1, 256},
         {"TMA tiled    4 col x 4096 rows (32 B rows), 1 buf, 1 CTA/SM", 1, 4096, 4, 1024, 1, 1, 256},
+        {"TMA tiled    4 col x 4096 rows (32 B rows), contiguous run per CTA", 1, 4096, 4, 1024, 1, 1, 256, 1},
+        {"TMA tiled    4 col x 4096 rows (32 B rows), groups of 2 CTAs interleave", 1, 4096, 4, 1024, 1, 1, 256, 2},
+        {"TMA tiled    4 col x 4096 rows (32 B rows), groups of 4 CTAs interleave", 1, 4096, 4, 1024, 1, 1, 256, 4},
+        {"TMA tiled    4 col x 4096 rows (32 B rows), groups of 8 CTAs interleave", 1, 4096, 4, 1024, 1, 1, 256, 8},
+        {"TMA tiled    8 col x 1024 rows (64 B rows), 1 buf, 2 CTA/SM, contiguous run", 1, 1024, 8, 512, 1, 2, 256, 1},
         {"cp.async4   wire, 8 col x 1024 rows, 1 buf, 2 CTA/SM", 2, 1024, 8, 512, 1, 2, 256},
         {"cp.async4   wire, 8 col x 1024 rows, 2 buf, 2 CTA/SM", 2, 1024, 8, 512, 2, 2, 256},
         {"TMA raw wire rows, 8 col x 1024 rows (96 B rows), 1 buf, 2 CTA/SM", 3, 1024, 8, 512, 1, 2, 256},
@@ -201,6 +224,7 @@ int main(int argc, char **argv)
         p.n_tiles = planes * p.tiles_per_plane;
         p.mode = c.mode;
         p.nbuf = c.nbuf;
+        p.assign = c.assign;
         p.sink = sink;
         CUtensorMap map{};
         if (c.mode == 1 || c.mode == 3) {
