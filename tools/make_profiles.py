@@ -35,7 +35,8 @@ open(os.path.join(P, f"{tag}_launches.md"), "w").write("\n".join(md) + "\n")
 rep = os.path.join(G, "prof_bench_stream.ncu-rep")
 run = lambda tool, *a: subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), rep, *a], capture_output=True, text=True).stdout
 open(os.path.join(P, f"{tag}_stream_ncu_summary.txt"), "w").write(
-    f"# ncu --set full --clock-control none --import-source on -k regex:chain_stream_kernel -s 4 -c 1 {CMD}\n" + run("ncu_summary.py"))
+    f"# ncu --set full --clock-control none --import-source on -k regex:chain_stream_kernel -s 4 -c 1 {CMD}\n"
+    "# (the same command exited 0 without ncu immediately before; one 143-sector launch of the planar streaming kernel)\n" + run("ncu_summary.py"))
 open(os.path.join(P, f"{tag}_stream_hot_sass.txt"), "w").write(
     "# stall reasons, instruction mix and the SASS instructions with most warp-stall samples of the launch above\n" + run("ncu_stalls.py", "40"))
 rr = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
