@@ -599,6 +599,35 @@ def run_ours(args):
     ms_copy = _max_over_ranks(_timed_launches(copy, 5, stream), dev, world) / 5
     h2d_ceiling_gbs = wire_np.nbytes / (ms_copy * 1e-3) / 1e9  # per GPU, with every rank copying
 
+    # ---- BASELINE config 2 ("single sector, all stages fused"): latency of ONE sector, N = 1 only ----
+    single = None
+    if world == 1:
+        sector_floats = C * M * N * 2
+        one = lambda k: chain.process_device(d_in.data_ptr() + (k * 7 % S) * sector_floats * 4, 1, d_out[0].data_ptr(),
+                                             stream.cuda_stream)
+        for k in range(5):
+            one(k)
+        dev_us = []
+        for k in range(60):  # a different resident sector every time: its 12.6 MB are not in L2
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            one(k)
+            b.record(stream)
+            b.synchronize()
+            dev_us.append(a.elapsed_time(b) * 1e3)
+        out_one = np.empty((1, M // 2, 2), dtype=np.float32)
+        host_us = []
+        for k in range(40):  # wire records in pinned host memory -> products in host memory, wall clock
+            view = pin_in.array[(k * 7 % S2) * M * N * 12:][:M * N * 12]
+            t0 = time.perf_counter()
+            wire_chain.process_host(view, 1, out_one)
+            host_us.append((time.perf_counter() - t0) * 1e6)
+        single = {"device_us": statistics.median(dev_us), "device_us_min": min(dev_us),
+                  "host_to_host_us": statistics.median(host_us), "host_to_host_us_min": min(host_us),
+                  "note": "one 1024x512x3 sector per call: HBM-resident planar input (CUDA events around one launch, input "
+                          "not in L2) and wire records from pinned host memory through wrp_process_host (wall clock, "
+                          "H2D 6.3 MB + one launch + D2H 4 KiB)"}
+
     # ---- side figure: the same batch resident in HBM in the wire format (int16 ingest) ----
     d_out2 = torch.empty((S2, M // 2, 2), dtype=torch.float32, device=dev)
     fw = lambda: wire_chain.process_device(d_wire.data_ptr(), S2, d_out2.data_ptr(), stream.cuda_stream)
@@ -662,6 +691,7 @@ def run_ours(args):
                                         "note": "streaming kernel: range tiles folded into per-gate sums, no range->Doppler "
                                                 "hand-off; stages 03-08 in energy form (Parseval)"},
                             **alt},
+            "single_sector": single,
             "stress": stress,
             "volume": volume,
             "roofline": {"bound": "hbm", "kernel": chain_kernel, "achieved": achieved, "peak": peak,

@@ -544,14 +544,14 @@ static int process_device_impl(wrp_handle *h, const void *dev_iq, int n_sectors,
                 if (h->wire3) {
                     if (!wrp::wire3_encode_tensor_map(h->tma_encode, &tmap, chain_in, N, S))
                         return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the wire batch (is the device buffer 16-byte aligned?)");
-                    CK(h, wrp::launch_wire3(p, h->stream_max_grid, tmap, st));
+                    CK(h, wrp::launch_wire3(p, h->stream_max_grid, h->sm_count, tmap, st));
                     h->launches++;
                     h->prof.sectors += h->profiling ? S : 0;
                     continue;
                 }
                 if (!wire_direct && !wrp::stream_encode_tensor_map(h->tma_encode, &tmap, chain_in, M, N, (long long)S * C, h->l2_promotion))
                     return fail(h, WRP_ERR_CUDA, "wrp_process_device: cuTensorMapEncodeTiled rejected the batch (is the device buffer 16-byte aligned?)");
-                CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, (c.debug & 32) != 0, tmap, st));
+                CK(h, wrp::launch_stream(p, M, wire_direct, h->stream_max_grid, h->sm_count, (c.debug & 32) != 0, tmap, st));
                 h->launches++;
             } else if (h->chain == wrp_handle::CHAIN_QUEUE) {
                 ProfScope ps(h, st, 4);

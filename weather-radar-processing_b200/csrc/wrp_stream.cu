@@ -28,6 +28,7 @@
 //          (partials in scratch, fixed order: results do not depend on arrival order).
 // Nothing in this kernel waits for another CTA: any grid size is correct, co-residency is irrelevant.
 #include "wrp_stream.h"
+#include <cstdlib>
 
 #include "wrp_fft.cuh"
 #include "wrp_internal.h"
@@ -594,10 +595,16 @@ __global__ void __launch_bounds__(Cfg<Q, WIRE>::THREADS, Q == 1 ? 2 : 1)
                     for (int r = 0; r < RPT; ++r)
 #pragma unroll
                         for (int q = 0; q < 7; ++q) vals[r][q] = 0.f;
+                    // every CTA after the first starts its run inside this plane (slot 0); the first one only if its
+                    // run begins exactly at the plane's first tile.  One sector alone is cut into NT parts per plane,
+                    // so this loop is the tail of the single-sector latency: no division in it, four parts' loads in
+                    // flight, the additions still in CTA order.  (Unrolled further, slot by slot with eight parts in
+                    // flight, it is no faster and the larger kernel image costs the full-batch rate 2 %.)
+                    const int first_slot = (int)(((long long)x_first * total / Gp) / p.NT) == vp ? 0 : 1;
+#pragma unroll 4
                     for (int x = x_first; x <= x_last; ++x) {
-                        const int x_vp_lo = (int)(((long long)x * total / Gp) / p.NT);
                         const float *part =
-                            p.scratch + ((size_t)(x * CG + grp) * 2 + (vp == x_vp_lo ? 0 : 1)) * 7 * hm;
+                            p.scratch + ((size_t)(x * CG + grp) * 2 + (x == x_first ? first_slot : 0)) * 7 * hm;
 #pragma unroll
                         for (int r = 0; r < RPT; ++r) {
                             const int k = slot_gate(r);
@@ -880,9 +887,11 @@ __global__ void __launch_bounds__(w3::THREADS, 1)
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
                         for (int q = 0; q < 7; ++q) vals[r][q] = 0.f;
+                    // (slot 0 for every CTA after the first: its run starts inside this sector — see chain_stream_kernel)
+                    const int first_slot = (int)(((long long)x_first * total / G) / NT) == sector ? 0 : 1;
+#pragma unroll 2
                     for (int x = x_first; x <= x_last; ++x) {
-                        const int x_sector_lo = (int)(((long long)x * total / G) / NT);
-                        const float *part = p.scratch + (((size_t)x * 2 + (sector == x_sector_lo ? 0 : 1)) * 3 + ch) * 7 * hm;
+                        const float *part = p.scratch + (((size_t)x * 2 + (x == x_first ? first_slot : 0)) * 3 + ch) * 7 * hm;
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             const int k = slot_gate(r);
@@ -974,7 +983,22 @@ bool wire3_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-cudaError_t launch_wire3(StreamParams p, int max_grid, const CUtensorMap &tmap, cudaStream_t st)
+// Grid of one launch.  Large batches take every CTA slot.  Small batches are latency problems: a CTA's tiles run back
+// to back (about 4 us each) and a plane cut into k parts costs its last arriver k partial-sum reads, so fewer CTAs with
+// more tiles each finish earlier — measured on B200 (profiles/r02_small_batch_grid.md): at least min_tiles tiles per CTA
+// (4 for the plane kernels, 8 for chain_wire3_kernel), and one CTA per SM as long as the full grid would hold fewer than
+// 6 tiles each.
+static long long pick_grid(long long total, long long max_grid, int sm_count, int min_tiles = 4)
+{
+    const long long g = max_grid < total ? max_grid : total;
+    const long long g4 = total / min_tiles > 0 ? total / min_tiles : 1;
+    if (sm_count < 1) sm_count = 1;
+    if (g4 <= sm_count) return g4 < g ? g4 : g;
+    if (total < 6 * max_grid && sm_count < g) return sm_count;
+    return g;
+}
+
+cudaError_t launch_wire3(StreamParams p, int max_grid, int sm_count, const CUtensorMap &tmap, cudaStream_t st)
 {
     if (p.S <= 0) return cudaSuccess;
     p.NT = p.N / 4;
@@ -982,7 +1006,7 @@ cudaError_t launch_wire3(StreamParams p, int max_grid, const CUtensorMap &tmap, 
     p.n_float = (float)p.N;
     p.chan_groups = 1;
     const long long total = (long long)p.S * p.NT;
-    const int grid = (int)(max_grid < total ? max_grid : total);
+    const int grid = (int)pick_grid(total, max_grid, sm_count, 8); // 12-column tiles, whole sectors combined by one CTA: 8 per CTA
     cudaError_t e = cudaMemsetAsync(p.plane_cnt, 0, sizeof(int) * (size_t)p.S, st); // parts of a cut sector that have arrived
     if (e != cudaSuccess) return e;
     stream::chain_wire3_kernel<<<grid, stream::w3::THREADS, stream::w3::SMEM, st>>>(p, tmap);
@@ -1019,8 +1043,8 @@ bool stream_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *bas
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, const CUtensorMap &tmap,
-                          cudaStream_t st)
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int sm_count, int channel_groups,
+                          const CUtensorMap &tmap, cudaStream_t st)
 {
     if (p.S <= 0) return cudaSuccess;
     const int T = M == 4096 ? 4 : 8;
@@ -1029,8 +1053,7 @@ cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int cha
     p.n_float = (float)p.N;
     p.chan_groups = (wire || channel_groups) ? p.C : 1;
     const long long total = (long long)(p.chan_groups == 1 ? p.S * p.C : p.S) * p.NT;
-    long long grid = max_grid / p.chan_groups;
-    if (grid > total) grid = total;
+    long long grid = pick_grid(total, max_grid / p.chan_groups, sm_count / p.chan_groups);
     grid *= p.chan_groups;
     cudaError_t e = cudaMemsetAsync(p.plane_cnt, 0, sizeof(int) * (size_t)p.S * (p.C + 1), st); // plane_cnt + sector_cnt
     if (e != cudaSuccess) return e;

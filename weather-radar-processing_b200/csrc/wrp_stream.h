@@ -48,8 +48,8 @@ size_t stream_scratch_floats(int M, int max_grid);
 // so that both formats associate their sums identically (bit-exactness tests of the decode)
 // tmap: planar input only — 2-D tensor map over the batch viewed as [S*C*M rows][N] 8-byte elements with
 // box {T columns, 8192 / (8 T) rows} (stream_encode_tensor_map); wire input passes a zeroed map
-cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int channel_groups, const CUtensorMap &tmap,
-                          cudaStream_t st);
+cudaError_t launch_stream(StreamParams p, int M, int wire, int max_grid, int sm_count, int channel_groups,
+                          const CUtensorMap &tmap, cudaStream_t st);
 // Encodes the tensor map of one launch (host-side, no CUDA call besides the driver's encoder).
 // encode_fn = cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (libwrp does not link libcuda).
 // l2_promotion_bytes: 0 / 64 / 128 / 256 — the tensor map's L2 promotion: a row segment narrower than that pulls the
@@ -63,6 +63,6 @@ const char *stream_kernel_name();
 cudaError_t wire3_setup(int sm_count, int *max_grid);
 size_t wire3_scratch_floats(int max_grid);
 bool wire3_encode_tensor_map(void *encode_fn, CUtensorMap *out, const void *base, int N, long long sectors);
-cudaError_t launch_wire3(StreamParams p, int max_grid, const CUtensorMap &tmap, cudaStream_t st);
+cudaError_t launch_wire3(StreamParams p, int max_grid, int sm_count, const CUtensorMap &tmap, cudaStream_t st);
 
 } // namespace wrp
