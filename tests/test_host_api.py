@@ -59,6 +59,22 @@ def test_no_cpu_fallback(wrp):
     assert ei.value.status == 3 and "no CPU fallback" in str(ei.value)
 
 
+def test_null_handles_are_rejected_not_dereferenced(wrp):
+    """Every entry point that takes a handle answers a NULL handle with WRP_ERR_INVALID (no CUDA call is made)."""
+    import ctypes as C
+    L = wrp.lib()
+    assert L.wrp_set_product_mirrors(None, None, 0) == 1
+    assert L.wrp_set_stage02_tap(None, None) == 1
+    assert L.wrp_process_device(None, None, 1, None, None) == 1
+    assert L.wrp_process_host(None, None, 1, None) == 1
+    assert L.wrp_process_host_to_device(None, None, 1, None) == 1
+    assert L.wrp_volume_process(None, None, None) == 1
+    first, n = C.c_int(0), C.c_int(0)
+    assert L.wrp_volume_shard(None, 0, C.byref(first), C.byref(n)) == 1
+    L.wrp_destroy(None)
+    L.wrp_volume_destroy(None)
+
+
 def test_product_packets_match_reference_layout(wrp, oracle):
     """send_results (rpv2.cu:620-663): [sector BE16][elev BE16][512 BE floats]; the stream
     variants drop the elevation (gpu_1fp_streamcasc.cu:709-716).  Float bytes per floats.c:3-10."""
